@@ -1,0 +1,173 @@
+/*
+ * ctr_b200.h -- C ABI of libctr_b200.so, the B200 (sm_100a) CTR feature-interaction engine.
+ *
+ * This is the drop-in boundary for the hot path of lambdaji/tf_repos'
+ * deep_ctr/Model_pipeline/*.py `model_fn`s.  The reference has no FFI of its own (it is
+ * TensorFlow-1.4 Python); each entry point below replaces the cluster of TF ops cited next to
+ * it (file:line relative to the reference checkout).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`;
+ *    tensors are contiguous row-major fp32 / int32 (ids may be int32 or int64, see id_bits);
+ *  - no allocation inside the library: scratch is caller-provided, sized by *_workspace_bytes();
+ *  - every call enqueues work on `stream` and returns immediately (no host sync, graph-capturable);
+ *  - return value: 0 = CTR_OK, <0 = ctr_status; text via ctr_last_error() (thread-local);
+ *  - no C++ exception crosses the ABI; no global mutable state except the launch counter.
+ */
+#ifndef CTR_B200_H_
+#define CTR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ctr_stream_t; /* a cudaStream_t / CUstream */
+
+enum ctr_status {
+  CTR_OK = 0,
+  CTR_ERR_INVALID_ARG = -1,
+  CTR_ERR_UNSUPPORTED = -2,
+  CTR_ERR_CUDA = -3,
+  CTR_ERR_WORKSPACE = -4
+};
+
+/* interaction modes of the embedding kernels */
+enum ctr_fm_mode {
+  CTR_FM_DEEPFM = 0, /* y_v[B] = 0.5*sum_k((sum_f e)^2 - sum_f e^2)        DeepFM.py:129-135 */
+  CTR_FM_NFM = 1,    /* bi[B,K] = 0.5*((sum_f e)^2 - sum_f e^2)            NFM.py:122-128    */
+  CTR_FM_PLAIN = 2   /* gather+scale only                                  DCN.py:135-138, PNN.py:134-136, AFM.py:128-130 */
+};
+
+enum ctr_optimizer {
+  CTR_OPT_ADAM = 0,     /* tf.train.AdamOptimizer      DeepFM.py:205 */
+  CTR_OPT_ADAGRAD = 1,  /* tf.train.AdagradOptimizer   DeepFM.py:207 */
+  CTR_OPT_MOMENTUM = 2, /* tf.train.MomentumOptimizer  DeepFM.py:209 */
+  CTR_OPT_FTRL = 3      /* tf.train.FtrlOptimizer      DeepFM.py:211 */
+};
+
+/* ---- library ------------------------------------------------------------------------------- */
+int ctr_abi_version(void);
+const char* ctr_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t ctr_launch_count(void);
+/* number of SMs the library sized its persistent grids for (148 on B200); <0 on error */
+int ctr_device_sm_count(void);
+
+/* ---- K1: gather + scale + FM first/second order + emit x ------------------------------------
+ * Replaces tf.nn.embedding_lookup(FM_W/FM_V) + multiply + reduce_sum/square chain,
+ * DeepFM.py:125-135,151 (NFM.py:118-128; plain gather DCN.py:135-138).
+ *   ids   [B,F]  int32 (id_bits=32) or int64 (id_bits=64); vals [B,F] f32
+ *   V     [N,K]  f32;   W [N] f32 or NULL (no first-order term)
+ *   x     [B,F*K] = V[ids]*vals            (NULL to skip; NFM does not need it)
+ *   y_w   [B]     = sum_f W[ids]*vals      (NULL iff W NULL)
+ *   y2    mode DEEPFM: [B]; mode NFM: [B,K]; mode PLAIN: ignored (may be NULL)
+ *   S     [B,K]   = sum_f e  (saved for the backward; NULL in PLAIN mode)
+ *   oob   optional int32[2] device word: {count, first bad id}; TF raises InvalidArgument for ids
+ *         outside [0,N) on CPU -- here such an occurrence contributes 0 and is counted.
+ */
+int ctr_fm_embed_fwd(const void* ids, int id_bits, const float* vals, const float* V, const float* W,
+                     int64_t N, int B, int F, int K, int mode, float* x, float* y_w, float* y2,
+                     float* S, int32_t* oob, ctr_stream_t stream);
+
+/* ---- K2: backward of K1 w.r.t. the gathered rows ---------------------------------------------
+ * Replaces the autodiff of DeepFM.py:125-135,151 that optimizer.minimize (DeepFM.py:213) builds:
+ * per-occurrence IndexedSlices values for FM_V and FM_W.
+ *   x   [B,F*K] the scaled embeddings saved by the forward;  S [B,K] saved by the forward
+ *   dX  [B,F*K] upstream grad of x (NULL = 0);  dy2: DEEPFM [B] upstream of y_v, NFM [B,K] of bi
+ *   dyw [B] upstream of y_w (NULL iff g_w NULL)
+ *   g_rows [B*F,K] = (dy2*(S-e) + dX) * val ;  g_w [B*F] = dyw*val
+ */
+int ctr_fm_embed_bwd(const float* vals, const float* x, const float* S, const float* dX,
+                     const float* dy2, const float* dyw, int B, int F, int K, int mode,
+                     float* g_rows, float* g_w, ctr_stream_t stream);
+
+/* ---- K3: de-duplication of IndexedSlices ------------------------------------------------------
+ * Replaces optimizer._deduplicate_indexed_slices = tf.unique + unsorted_segment_sum that
+ * optimizer.minimize applies to the embedding gradients (DeepFM.py:213, [TF-sem]).
+ * Stable LSD radix sort of (id, position), then run-length encoding.  Integer outputs are
+ * bit-exact w.r.t. numpy.unique(return_inverse=True) + a stable argsort:
+ *   perm        [n]  positions 0..n-1 sorted by (id, position)
+ *   uniq        [n]  ascending distinct ids (first *n_uniq valid)
+ *   inverse     [n]  inverse[p] = index into uniq of ids[p]
+ *   seg_offsets [n+1] run starts in the sorted order; seg_offsets[*n_uniq] = n
+ *   n_uniq      int32[1] device scalar
+ *   long_list   int32[n+1] scratch-out: [0] = number of runs longer than CTR_LONG_SEG, then their
+ *               uniq indices (consumed by ctr_segment_sum_rows)
+ */
+#define CTR_LONG_SEG 128
+size_t ctr_unique_segment_workspace_bytes(int64_t n, int64_t N);
+int ctr_unique_segment(const int32_t* ids, int64_t n, int64_t N, int32_t* perm, int32_t* uniq,
+                       int32_t* inverse, int32_t* seg_offsets, int32_t* n_uniq, int32_t* long_list,
+                       void* ws, size_t ws_bytes, ctr_stream_t stream);
+
+/* g_uniq[u,:] = sum over the run u of g_rows[perm[i],:]  (fixed-shape trees: deterministic).
+ * g_w / gw_uniq are the optional scalar column of the first-order table (NULL to skip). */
+int ctr_segment_sum_rows(const float* g_rows, const float* g_w, const int32_t* perm,
+                         const int32_t* seg_offsets, const int32_t* n_uniq,
+                         const int32_t* long_list, int64_t n, int K, float* g_uniq, float* gw_uniq,
+                         ctr_stream_t stream);
+
+/* ---- K4: optimizer apply on table rows ---------------------------------------------------------
+ * TF-1.x arithmetic, [TF-sem] (see oracle/tf_semantics.py for the restatement and its sources).
+ * `hyper` is a DEVICE float[8]: {lr_t, beta1, beta2, eps, l2_reg, aux0, aux1, aux2} so that a
+ * captured CUDA graph can be replayed while the step counter advances.
+ *   Adam:     lr_t = lr*sqrt(1-b2^t)/(1-b1^t) precomputed (ctr_adam_tick);
+ *   Adagrad:  lr_t = lr;            slot0 = accumulator
+ *   Momentum: lr_t = lr; aux0 = momentum; slot0 = accumulator
+ *   Ftrl:     lr_t = lr; aux0 = lr_power, aux1 = l1, aux2 = l2(ftrl);  slot0 = accum, slot1 = linear
+ *
+ * sparse apply: rows uniq[0..*n_uniq) get g = g_uniq + l2_reg*var and the optimizer's *sparse*
+ * update.  If stage != NULL the new (var, slot0, slot1) rows are written to stage[3][n][K]
+ * instead of in place (exact mode: the dense sweep runs next, then ctr_opt_patch_rows).
+ */
+int ctr_opt_sparse_rows(int opt, float* var, float* slot0, float* slot1, const int32_t* uniq,
+                        const int32_t* n_uniq, const float* g_uniq, int64_t n_max, int K,
+                        const float* hyper, float* stage, ctr_stream_t stream);
+/* dense sweep: every one of the n_elem elements takes the step with g = l2_reg*var (what TF does
+ * to rows no gather touched, because l2_loss densifies the gradient and sparse Adam decays every
+ * row).  Also accumulates sum(var_old^2) into sumsq_partials[grid] (for tf.nn.l2_loss in the
+ * loss, DeepFM.py:189-190) when non-NULL; *n_partials returns the number written. */
+int ctr_opt_dense_sweep(int opt, float* var, float* slot0, float* slot1, int64_t n_elem,
+                        const float* hyper, float* sumsq_partials, int* n_partials_host,
+                        ctr_stream_t stream);
+int ctr_opt_patch_rows(float* var, float* slot0, float* slot1, const int32_t* uniq,
+                       const int32_t* n_uniq, const float* stage, int64_t n_max, int K, int n_slots,
+                       ctr_stream_t stream);
+/* dense variables with an explicit gradient (MLP weights, biases, fm_bias, cross_w/b):
+ * TF's fused ApplyAdam/ApplyAdagrad/ApplyMomentum/ApplyFtrl kernels; g += l2_reg*var first when
+ * l2_reg (hyper[4]) != 0. */
+int ctr_opt_dense_grad(int opt, float* var, float* slot0, float* slot1, const float* grad,
+                       int64_t n_elem, const float* hyper, ctr_stream_t stream);
+/* Called once at the start of a step: lr_t = lr*sqrt(1-b2p)/(1-b1p) from the CURRENT beta powers is
+ * written to hyper[8*r] for r < n_hyper (consecutive hyper records: tables, dense variables ...),
+ * then the powers advance the way AdamOptimizer._finish does (fp32 running products) and the step
+ * counter increments.  state = device float[4] {beta1_power, beta2_power, lr, global_step}. */
+int ctr_adam_tick(float* state, float* hyper, int n_hyper, ctr_stream_t stream);
+/* deterministic sum of n floats -> out[0] (two-level fixed tree) ; scale applied at the end */
+int ctr_reduce_sum(const float* in, int64_t n, float scale, float* out, float* ws, size_t ws_bytes,
+                   ctr_stream_t stream);
+/* 0.5*sum(t^2) (tf.nn.l2_loss) of a whole tensor, deterministic */
+size_t ctr_l2_loss_workspace_bytes(int64_t n);
+int ctr_l2_loss(const float* t, int64_t n, float* out, void* ws, size_t ws_bytes, ctr_stream_t stream);
+
+/* ---- loss head -----------------------------------------------------------------------------------
+ * y = ((bias + y_a) + y_b) + y_c (NULL terms skipped; DeepFM.py:172-175), pred = sigmoid(y)
+ * (:176), loss_ce = mean(max(y,0) - y*t + log1p(exp(-|y|))) (:188), dy = (pred - t)/B,
+ * dbias = sum(dy).  labels NULL => inference (only y, pred).
+ */
+int ctr_logit_loss(const float* bias, const float* y_a, const float* y_b, const float* y_c,
+                   const float* labels, int B, float* y, float* pred, float* loss_ce, float* dy,
+                   float* dbias, ctr_stream_t stream);
+
+/* ---- table initialisation (glorot_normal_initializer, DeepFM.py:115-116; truncated at 2 sigma) --- */
+int ctr_init_trunc_normal(float* t, int64_t n, float stddev, uint64_t seed, ctr_stream_t stream);
+int ctr_fill(float* t, int64_t n, float value, ctr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTR_B200_H_ */

@@ -1,0 +1,190 @@
+"""Thin torch-tensor wrappers over the C ABI (include/ctr_b200.h).
+
+PyTorch is used here only for device memory and streams: every function passes raw device
+pointers and the current CUDA stream to libctr_b200.so.  No function in this module computes
+anything with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import CtrError, check
+
+FM_DEEPFM, FM_NFM, FM_PLAIN = 0, 1, 2
+OPT_ADAM, OPT_ADAGRAD, OPT_MOMENTUM, OPT_FTRL = 0, 1, 2, 3
+OPT_BY_NAME = {"Adam": OPT_ADAM, "Adagrad": OPT_ADAGRAD, "Momentum": OPT_MOMENTUM, "ftrl": OPT_FTRL}
+OPT_SLOTS = {OPT_ADAM: 2, OPT_ADAGRAD: 1, OPT_MOMENTUM: 1, OPT_FTRL: 2}
+LONG_SEG = 128
+
+_L = _lib.raw()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor], dtype=None, name="tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CtrError(f"{name} must be a CUDA tensor (no CPU fallback exists)")
+    if not t.is_contiguous():
+        raise CtrError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise CtrError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def fm_embed_fwd(ids, vals, V, W, mode, x=None, y_w=None, y2=None, S=None, oob=None):
+    """K1.  ids [B,F] int32|int64, vals [B,F] f32, V [N,K], W [N]|None.  Outputs are caller-allocated."""
+    B, F = ids.shape
+    N, K = V.shape
+    if ids.dtype == torch.int32:
+        bits = 32
+    elif ids.dtype == torch.int64:
+        bits = 64
+    else:
+        raise CtrError(f"ids must be int32 or int64, got {ids.dtype}")
+    check(
+        _L.ctr_fm_embed_fwd(
+            _p(ids, None, "ids"), bits, _p(vals, torch.float32, "vals"), _p(V, torch.float32, "V"),
+            _p(W, torch.float32, "W"), N, B, F, K, mode, _p(x, torch.float32, "x"),
+            _p(y_w, torch.float32, "y_w"), _p(y2, torch.float32, "y2"), _p(S, torch.float32, "S"),
+            _p(oob, torch.int32, "oob"), _stream()),
+        "ctr_fm_embed_fwd")
+
+
+def fm_embed_bwd(vals, x, S, dX, dy2, dyw, K, mode, g_rows, g_w=None):
+    B, F = vals.shape
+    check(
+        _L.ctr_fm_embed_bwd(
+            _p(vals, torch.float32, "vals"), _p(x, torch.float32, "x"), _p(S, torch.float32, "S"),
+            _p(dX, torch.float32, "dX"), _p(dy2, torch.float32, "dy2"), _p(dyw, torch.float32, "dyw"),
+            B, F, K, mode, _p(g_rows, torch.float32, "g_rows"), _p(g_w, torch.float32, "g_w"),
+            _stream()),
+        "ctr_fm_embed_bwd")
+
+
+def unique_segment_workspace_bytes(n: int, N: int) -> int:
+    return int(_L.ctr_unique_segment_workspace_bytes(n, N))
+
+
+class UniqueWorkspace:
+    """Caller-owned buffers for K3 (allocated once, reused every step; graph-capture friendly)."""
+
+    def __init__(self, n: int, N: int, device):
+        self.n, self.N = n, N
+        i32 = dict(dtype=torch.int32, device=device)
+        self.perm = torch.empty(max(n, 1), **i32)
+        self.uniq = torch.empty(max(n, 1), **i32)
+        self.inverse = torch.empty(max(n, 1), **i32)
+        self.seg_offsets = torch.empty(n + 1, **i32)
+        self.n_uniq = torch.zeros(1, **i32)
+        self.long_list = torch.zeros(n + 1, **i32)
+        self.ws = torch.empty(max(unique_segment_workspace_bytes(n, N), 16), dtype=torch.uint8, device=device)
+
+
+def unique_segment(ids_flat: torch.Tensor, uw: UniqueWorkspace) -> None:
+    n = ids_flat.numel()
+    if n != uw.n:
+        raise CtrError(f"workspace was sized for n={uw.n}, got {n}")
+    check(
+        _L.ctr_unique_segment(
+            _p(ids_flat, torch.int32, "ids"), n, uw.N, _p(uw.perm), _p(uw.uniq), _p(uw.inverse),
+            _p(uw.seg_offsets), _p(uw.n_uniq), _p(uw.long_list), _p(uw.ws), uw.ws.numel(), _stream()),
+        "ctr_unique_segment")
+
+
+def segment_sum_rows(g_rows, g_w, uw: UniqueWorkspace, K, g_uniq, gw_uniq=None):
+    check(
+        _L.ctr_segment_sum_rows(
+            _p(g_rows, torch.float32, "g_rows"), _p(g_w, torch.float32, "g_w"), _p(uw.perm),
+            _p(uw.seg_offsets), _p(uw.n_uniq), _p(uw.long_list), uw.n, K,
+            _p(g_uniq, torch.float32, "g_uniq"), _p(gw_uniq, torch.float32, "gw_uniq"), _stream()),
+        "ctr_segment_sum_rows")
+
+
+def opt_sparse_rows(opt, var, slot0, slot1, uniq, n_uniq, g_uniq, n_max, K, hyper, stage=None):
+    check(
+        _L.ctr_opt_sparse_rows(
+            opt, _p(var, torch.float32, "var"), _p(slot0, torch.float32, "slot0"),
+            _p(slot1, torch.float32, "slot1"), _p(uniq, torch.int32, "uniq"),
+            _p(n_uniq, torch.int32, "n_uniq"), _p(g_uniq, torch.float32, "g_uniq"), n_max, K,
+            _p(hyper, torch.float32, "hyper"), _p(stage, torch.float32, "stage"), _stream()),
+        "ctr_opt_sparse_rows")
+
+
+def opt_dense_sweep(opt, var, slot0, slot1, hyper, sumsq_partials=None) -> int:
+    n_part = ctypes.c_int(0)
+    check(
+        _L.ctr_opt_dense_sweep(
+            opt, _p(var, torch.float32, "var"), _p(slot0, torch.float32, "slot0"),
+            _p(slot1, torch.float32, "slot1"), var.numel(), _p(hyper, torch.float32, "hyper"),
+            _p(sumsq_partials, torch.float32, "sumsq_partials"), ctypes.byref(n_part), _stream()),
+        "ctr_opt_dense_sweep")
+    return n_part.value
+
+
+def sweep_partials_count() -> int:
+    return int(_L.ctr_device_sm_count()) * 8
+
+
+def opt_patch_rows(var, slot0, slot1, uniq, n_uniq, stage, n_max, K, n_slots):
+    check(
+        _L.ctr_opt_patch_rows(
+            _p(var, torch.float32), _p(slot0, torch.float32), _p(slot1, torch.float32),
+            _p(uniq, torch.int32), _p(n_uniq, torch.int32), _p(stage, torch.float32), n_max, K,
+            n_slots, _stream()),
+        "ctr_opt_patch_rows")
+
+
+def opt_dense_grad(opt, var, slot0, slot1, grad, hyper):
+    check(
+        _L.ctr_opt_dense_grad(
+            opt, _p(var, torch.float32, "var"), _p(slot0, torch.float32, "slot0"),
+            _p(slot1, torch.float32, "slot1"), _p(grad, torch.float32, "grad"), var.numel(),
+            _p(hyper, torch.float32, "hyper"), _stream()),
+        "ctr_opt_dense_grad")
+
+
+def adam_tick(state, hyper):
+    """hyper: [n_hyper, 8] float32"""
+    check(_L.ctr_adam_tick(_p(state, torch.float32, "state"), _p(hyper, torch.float32, "hyper"),
+                           hyper.numel() // 8, _stream()), "ctr_adam_tick")
+
+
+def reduce_sum(inp, scale, out, ws):
+    check(
+        _L.ctr_reduce_sum(_p(inp, torch.float32, "in"), inp.numel(), float(scale), _p(out, torch.float32, "out"),
+                          _p(ws, torch.float32, "ws"), ws.numel() * 4, _stream()),
+        "ctr_reduce_sum")
+
+
+def l2_loss(t, out, ws):
+    check(
+        _L.ctr_l2_loss(_p(t, torch.float32, "t"), t.numel(), _p(out, torch.float32, "out"), _p(ws), ws.numel() * ws.element_size(),
+                       _stream()),
+        "ctr_l2_loss")
+
+
+def logit_loss(bias, y_a, y_b, y_c, labels, B, y=None, pred=None, loss_ce=None, dy=None, dbias=None):
+    check(
+        _L.ctr_logit_loss(
+            _p(bias, torch.float32, "bias"), _p(y_a, torch.float32, "y_a"), _p(y_b, torch.float32, "y_b"),
+            _p(y_c, torch.float32, "y_c"), _p(labels, torch.float32, "labels"), B,
+            _p(y, torch.float32, "y"), _p(pred, torch.float32, "pred"), _p(loss_ce, torch.float32, "loss_ce"),
+            _p(dy, torch.float32, "dy"), _p(dbias, torch.float32, "dbias"), _stream()),
+        "ctr_logit_loss")
+
+
+def init_trunc_normal(t, stddev: float, seed: int):
+    check(_L.ctr_init_trunc_normal(_p(t, torch.float32, "t"), t.numel(), float(stddev), int(seed), _stream()),
+          "ctr_init_trunc_normal")
+
+
+def fill(t, value: float):
+    check(_L.ctr_fill(_p(t, torch.float32, "t"), t.numel(), float(value), _stream()), "ctr_fill")
