@@ -181,7 +181,7 @@ class OracleModel:
                 m[uniq] = m[uniq] + summed * (one - b1)
                 v.mul_(b2)
                 v[uniq] = v[uniq] + (summed * summed) * (one - b2)
-                var.sub_((lr_t * m) / (torch.sqrt(v) + eps))
+                var.sub_((lr_t * m) / (tfs.ieee_sqrt(v) + eps))
             else:
                 rv = var[uniq]
                 rs = [s[uniq] for s in slots]

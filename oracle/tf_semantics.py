@@ -177,6 +177,19 @@ def f32(x) -> torch.Tensor:
     return torch.tensor(x, dtype=F32)
 
 
+# torch's CPU sqrt goes through MKL VML and is NOT correctly rounded (0.7 % of random fp32 inputs
+# differ from IEEE by 1 ulp, measured); numpy's is (hardware sqrtps).  Parity runs need the IEEE
+# result (the CUDA kernels use __fsqrt_rn); the timed cpu_baseline may flip FAST_SQRT to use all
+# host threads.
+FAST_SQRT = False
+
+
+def ieee_sqrt(t: torch.Tensor) -> torch.Tensor:
+    if FAST_SQRT or t.dtype != F32:
+        return torch.sqrt(t)
+    return torch.from_numpy(np.atleast_1d(np.sqrt(t.detach().numpy()))).reshape(t.shape)
+
+
 class AdamHyper:
     """tf.train.AdamOptimizer(learning_rate, 0.9, 0.999, 1e-8) (DeepFM.py:205) [TF-sem].
     beta{1,2}_power are fp32 variables initialised to beta{1,2} and multiplied by beta{1,2} in
@@ -194,7 +207,7 @@ class AdamHyper:
     def lr_t(self) -> torch.Tensor:
         """lr * sqrt(1 - beta2_power) / (1 - beta1_power), evaluated left to right in fp32."""
         one = torch.tensor(1.0, dtype=self.dtype)
-        return (self.lr * torch.sqrt(one - self.b2p)) / (one - self.b1p)
+        return (self.lr * ieee_sqrt(one - self.b2p)) / (one - self.b1p)
 
     def finish(self):
         self.b1p = self.b1p * self.b1
@@ -209,7 +222,7 @@ def adam_sparse_(var, m, v, g, lr_t, b1, b2, eps):
     one = torch.ones((), dtype=var.dtype)
     m.mul_(b1).add_(g * (one - b1))
     v.mul_(b2).add_((g * g) * (one - b2))
-    var.sub_((lr_t * m) / (torch.sqrt(v) + eps))
+    var.sub_((lr_t * m) / (ieee_sqrt(v) + eps))
 
 
 def adam_dense_(var, m, v, g, lr_t, b1, b2, eps):
@@ -218,14 +231,14 @@ def adam_dense_(var, m, v, g, lr_t, b1, b2, eps):
     one = torch.ones((), dtype=var.dtype)
     m.add_((g - m) * (one - b1))
     v.add_((g * g - v) * (one - b2))
-    var.sub_((m * lr_t) / (torch.sqrt(v) + eps))
+    var.sub_((m * lr_t) / (ieee_sqrt(v) + eps))
 
 
 def adagrad_(var, acc, g, lr):
     """ApplyAdagrad / SparseApplyAdagrad [TF-sem] (DeepFM.py:207; initial_accumulator_value=1e-8):
         acc += g*g ; var -= lr*g*rsqrt(acc)   (rsqrt restated as 1/sqrt, both IEEE)"""
     acc.add_(g * g)
-    var.sub_((lr * g) * (torch.ones((), dtype=var.dtype) / torch.sqrt(acc)))
+    var.sub_((lr * g) * (torch.ones((), dtype=var.dtype) / ieee_sqrt(acc)))
 
 
 def momentum_(var, acc, g, lr, momentum):
@@ -244,7 +257,7 @@ def ftrl_(var, accum, linear, g, lr, lr_power=-0.5, l1=0.0, l2=0.0):
     l2t = torch.tensor(l2, dtype=dt)
     new_accum = accum + g * g
     if lr_power == -0.5:
-        pn, po = torch.sqrt(new_accum), torch.sqrt(accum)
+        pn, po = ieee_sqrt(new_accum), ieee_sqrt(accum)
     else:
         pn, po = torch.pow(new_accum, -lr_power), torch.pow(accum, -lr_power)
     linear.add_(g - ((pn - po) / lr) * var)

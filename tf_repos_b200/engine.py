@@ -106,6 +106,7 @@ class SparseUpdater:
         self.red_ws = torch.empty(1024, **f32)
         # [l2*l2_loss(V), l2*l2_loss(W)] of the PRE-step tables (what `loss` of this step contains)
         self.reg = torch.zeros(2, **f32)
+        self.sweep_events = None  # set to [] to collect (start, end) CUDA events around the V sweep
 
     def dedup(self, ids_flat: torch.Tensor, g_rows: torch.Tensor, g_w: Optional[torch.Tensor]):
         ops.unique_segment(ids_flat, self.uw)
@@ -124,7 +125,14 @@ class SparseUpdater:
             ops.opt_sparse_rows(o.opt, t.var, t.slot(0), t.slot(1), uw.uniq, uw.n_uniq, g, n, t.K, hyper,
                                 stage if sweep else None)
             if sweep:
+                ev = None
+                if self.sweep_events is not None and ri == 0:  # bench.py: time the dominant kernel live
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
                 ops.opt_dense_sweep(o.opt, t.var, t.slot(0), t.slot(1), hyper, partials)
+                if ev is not None:
+                    ev[1].record()
+                    self.sweep_events.append(ev)
                 ops.opt_patch_rows(t.var, t.slot(0), t.slot(1), uw.uniq, uw.n_uniq, stage, n, t.K, o.n_slots)
                 ops.reduce_sum(partials, 0.5 * l2_reg, self.reg[ri:ri + 1], self.red_ws)
 
