@@ -156,12 +156,13 @@ int ctr_l2_loss(const float* t, int64_t n, float* out, void* ws, size_t ws_bytes
 
 /* ---- loss head -----------------------------------------------------------------------------------
  * y = ((bias + y_a) + y_b) + y_c (NULL terms skipped; DeepFM.py:172-175), pred = sigmoid(y)
- * (:176), loss_ce = mean(max(y,0) - y*t + log1p(exp(-|y|))) (:188), dy = (pred - t)/B,
- * dbias = sum(dy).  labels NULL => inference (only y, pred).
+ * (:176), loss_ce = sum(max(y,0) - y*t + log1p(exp(-|y|)))/B_total (:188), dy = (pred - t)/B_total,
+ * dbias = sum(dy).  B_total = B on one GPU; the global batch under data parallelism (the per-rank
+ * loss_ce / dbias / gradients then SUM to the global mean).  labels NULL => inference (y, pred only).
  */
 int ctr_logit_loss(const float* bias, const float* y_a, const float* y_b, const float* y_c,
-                   const float* labels, int B, float* y, float* pred, float* loss_ce, float* dy,
-                   float* dbias, ctr_stream_t stream);
+                   const float* labels, int B, int B_total, float* y, float* pred, float* loss_ce,
+                   float* dy, float* dbias, ctr_stream_t stream);
 
 /* ---- table initialisation (glorot_normal_initializer, DeepFM.py:115-116; truncated at 2 sigma) --- */
 int ctr_init_trunc_normal(float* t, int64_t n, float stddev, uint64_t seed, ctr_stream_t stream);

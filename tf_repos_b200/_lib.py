@@ -49,7 +49,7 @@ SIGNATURES = {
     "ctr_reduce_sum": (c_int, [P, c_int64, c_float, P, P, c_size_t, P]),
     "ctr_l2_loss_workspace_bytes": (c_size_t, [c_int64]),
     "ctr_l2_loss": (c_int, [P, c_int64, P, P, c_size_t, P]),
-    "ctr_logit_loss": (c_int, [P, P, P, P, P, c_int, P, P, P, P, P, P]),
+    "ctr_logit_loss": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P]),
     "ctr_init_trunc_normal": (c_int, [P, c_int64, c_float, c_uint64, P]),
     "ctr_fill": (c_int, [P, c_int64, c_float, P]),
 }

@@ -26,12 +26,12 @@ __device__ __forceinline__ float block_sum_1024(float v, float* sh) {
 __global__ void __launch_bounds__(LOSS_THREADS)
 logit_loss_kernel(const float* __restrict__ bias, const float* __restrict__ y_a,
                   const float* __restrict__ y_b, const float* __restrict__ y_c,
-                  const float* __restrict__ labels, int B, float* __restrict__ y_out,
+                  const float* __restrict__ labels, int B, int B_total, float* __restrict__ y_out,
                   float* __restrict__ pred, float* __restrict__ loss_ce, float* __restrict__ dy,
                   float* __restrict__ dbias) {
   __shared__ float sh[32];
   const float b0 = bias ? bias[0] : 0.f;
-  const float invB = __fdiv_rn(1.f, (float)B);
+  const float invB = __fdiv_rn(1.f, (float)B_total);  // mean over the GLOBAL batch (data parallel)
   float lsum = 0.f, dsum = 0.f;
   for (int i = threadIdx.x; i < B; i += LOSS_THREADS) {
     float y = b0;                       // left-to-right like the reference expression
@@ -65,12 +65,12 @@ logit_loss_kernel(const float* __restrict__ bias, const float* __restrict__ y_a,
 using namespace ctr;
 
 extern "C" int ctr_logit_loss(const float* bias, const float* y_a, const float* y_b, const float* y_c,
-                              const float* labels, int B, float* y, float* pred, float* loss_ce,
-                              float* dy, float* dbias, ctr_stream_t stream) {
-  CTR_REQUIRE(B >= 0, CTR_ERR_INVALID_ARG, "ctr_logit_loss: B < 0");
+                              const float* labels, int B, int B_total, float* y, float* pred,
+                              float* loss_ce, float* dy, float* dbias, ctr_stream_t stream) {
+  CTR_REQUIRE(B >= 0 && B_total >= B, CTR_ERR_INVALID_ARG, "ctr_logit_loss: need 0 <= B <= B_total");
   if (B == 0) return CTR_OK;
   CTR_REQUIRE(y_a || y_b || y_c, CTR_ERR_INVALID_ARG, "ctr_logit_loss: no logit term given");
-  logit_loss_kernel<<<1, LOSS_THREADS, 0, as_stream(stream)>>>(bias, y_a, y_b, y_c, labels, B, y, pred,
+  logit_loss_kernel<<<1, LOSS_THREADS, 0, as_stream(stream)>>>(bias, y_a, y_b, y_c, labels, B, B_total, y, pred,
                                                                loss_ce, dy, dbias);
   CTR_LAUNCHED("ctr_logit_loss");
   return CTR_OK;

@@ -33,13 +33,17 @@ class DeepFM:
     def __init__(self, field_size: int, feature_size: int, embedding_size: int, batch_size: int,
                  deep_layers="256,128,64", dropout="0.5,0.5,0.5", l2_reg: float = 1e-4,
                  learning_rate: float = 5e-4, optimizer: str = "Adam", update_mode: str = "exact",
-                 device="cuda", seed: int = 0, init_tables: bool = True):
+                 device="cuda", seed: int = 0, world: int = 1):
         assert update_mode in ("exact", "lazy")
         self.F, self.N, self.K, self.B = field_size, feature_size, embedding_size, batch_size
         self.layers, self.keep = _ints(deep_layers), _floats(dropout)
         self.l2_reg, self.update_mode = float(l2_reg), update_mode
         self.device = torch.device(device)
         dev = self.device
+        # data parallel (world > 1): tables are replicated; every rank all-gathers the per-occurrence
+        # sparse gradients and applies the identical de-duplicated update (synchronous DP replaces the
+        # reference's asynchronous parameter server, DeepFM.py:237-282 -- documented deviation)
+        self.world = world
         self.opt = OptimizerState(optimizer, learning_rate, l2_reg, dev)
         # ---- variables (DeepFM.py:114-116) ------------------------------------------------------
         self.fm_v = Table("fm_v", self.N, self.K, self.opt, dev, seed=seed * 2 + 1)
@@ -57,12 +61,17 @@ class DeepFM:
         self.y = torch.empty(B, **f32)
         self.pred = torch.empty(B, **f32)
         self.dy = torch.empty(B, **f32)
-        self.loss_ce = torch.zeros(1, **f32)
+        self.loss_ce = self.dense.tail[0:1]
         self.g_rows = torch.empty(B * F, K, **f32)
         self.g_w = torch.empty(B * F, **f32)
         self.oob = torch.zeros(2, dtype=torch.int32, device=dev)
         self.d_last = torch.empty(B, self.mlp.out_in, **f32)
-        self.updater = SparseUpdater(B * F, self.N, K, self.opt, dev, with_scalar_table=True)
+        G = world
+        self.updater = SparseUpdater(G * B * F, self.N, K, self.opt, dev, with_scalar_table=True)
+        if G > 1:
+            self.ids_all = torch.empty(G * B * F, dtype=torch.int32, device=dev)
+            self.g_rows_all = torch.empty(G * B * F, K, **f32)
+            self.g_w_all = torch.empty(G * B * F, **f32)
         self.global_step = 0
 
     # ---- variable access by TF name ------------------------------------------------------------------
@@ -109,11 +118,19 @@ class DeepFM:
         self.opt.tick()
         a, y_d = self._forward(ids, vals, train=True, masks=masks)
         ops.logit_loss(self.dense["fm_bias"], self.y_w, self.y_v, y_d, labels, B, y=self.y, pred=self.pred,
-                       loss_ce=self.loss_ce, dy=self.dy, dbias=self.dense.grads["fm_bias"])
+                       loss_ce=self.loss_ce, dy=self.dy, dbias=self.dense.grads["fm_bias"], B_total=B * self.world)
         self.mlp.backward_out(a, self.dy, self.dense, self.d_last)
         dX = self.mlp.backward_hidden(self.x, self.d_last, self.dense)
         ops.fm_embed_bwd(vals, self.x, self.S, dX, self.dy, self.dy, K, ops.FM_DEEPFM, self.g_rows, self.g_w)
-        self.updater.dedup(ids.view(-1), self.g_rows, self.g_w)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.ids_all, ids.reshape(-1))
+            dist.all_gather_into_tensor(self.g_rows_all, self.g_rows)
+            dist.all_gather_into_tensor(self.g_w_all, self.g_w)
+            dist.all_reduce(self.dense.grad)  # dense gradients + the loss tail, summed over ranks
+            self.updater.dedup(self.ids_all, self.g_rows_all, self.g_w_all)
+        else:
+            self.updater.dedup(ids.reshape(-1), self.g_rows, self.g_w)
         self.updater.apply(self.fm_v, self.fm_w, exact=(self.update_mode == "exact"), l2_reg=self.l2_reg)
         self.dense.apply()
         self.global_step += 1

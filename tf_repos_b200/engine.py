@@ -142,7 +142,7 @@ class DenseVars:
     optimizer apply is a single launch.  Views keep the TF variable names."""
 
     def __init__(self, specs: Sequence[Tuple[str, Tuple[int, ...]]], opt: OptimizerState, device,
-                 l2_names: Sequence[str] = ()):
+                 l2_names: Sequence[str] = (), tail: int = 4):
         # variables with L2 first, so each group is one contiguous range
         specs = [s for s in specs if s[0] in l2_names] + [s for s in specs if s[0] not in l2_names]
         self.opt = opt
@@ -156,7 +156,10 @@ class DenseVars:
         self.n_l2 = sum(pad(sz) for (nm, _), sz in zip(specs, sizes) if nm in l2_names)
         f32 = dict(dtype=torch.float32, device=device)
         self.flat = torch.zeros(max(self.total, 4), **f32)
-        self.grad = torch.zeros(max(self.total, 4), **f32)
+        # `tail` extra floats ride along in the gradient buffer (per-rank loss terms) so that ONE
+        # all-reduce covers dense gradients + loss under data parallelism
+        self.grad = torch.zeros(max(self.total, 4) + tail, **f32)
+        self.tail = self.grad[max(self.total, 4):]
         self.slots = []
         for s in range(opt.n_slots):
             t = torch.empty(max(self.total, 4), **f32)

@@ -171,11 +171,11 @@ def l2_loss(t, out, ws):
         "ctr_l2_loss")
 
 
-def logit_loss(bias, y_a, y_b, y_c, labels, B, y=None, pred=None, loss_ce=None, dy=None, dbias=None):
+def logit_loss(bias, y_a, y_b, y_c, labels, B, y=None, pred=None, loss_ce=None, dy=None, dbias=None, B_total=None):
     check(
         _L.ctr_logit_loss(
             _p(bias, torch.float32, "bias"), _p(y_a, torch.float32, "y_a"), _p(y_b, torch.float32, "y_b"),
-            _p(y_c, torch.float32, "y_c"), _p(labels, torch.float32, "labels"), B,
+            _p(y_c, torch.float32, "y_c"), _p(labels, torch.float32, "labels"), B, B_total or B,
             _p(y, torch.float32, "y"), _p(pred, torch.float32, "pred"), _p(loss_ce, torch.float32, "loss_ce"),
             _p(dy, torch.float32, "dy"), _p(dbias, torch.float32, "dbias"), _stream()),
         "ctr_logit_loss")
