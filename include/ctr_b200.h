@@ -154,6 +154,34 @@ int ctr_reduce_sum(const float* in, int64_t n, float scale, float* out, float* w
 size_t ctr_l2_loss_workspace_bytes(int64_t n);
 int ctr_l2_loss(const float* t, int64_t n, float* out, void* ws, size_t ws_bytes, ctr_stream_t stream);
 
+/* ---- K4': exact-deferred ("epoch") table update ---------------------------------------------------
+ * Same results, bit for bit, as ctr_opt_sparse_rows(stage) + ctr_opt_dense_sweep + ctr_opt_patch_rows
+ * every step, at 1/P of the HBM traffic: the update TF gives a row that nothing gathered
+ * (g = l2_reg*var, DeepFM.py:189-190 + non-lazy sparse Adam, [TF-sem]) is an element-wise recurrence,
+ * so it is replayed lazily -- when a batch gathers the row (ctr_epoch_rows) or once per epoch of P
+ * steps for all rows in one pass over HBM (ctr_epoch_sweep).
+ *   last      uint8[N] per row: steps of the current epoch already applied to the stored state
+ *   lr_table  device float[ctr_epoch_max_steps()]: lr_t of every step of the current epoch
+ *   ss        device double[ctr_epoch_max_steps()]: sum(var^2) seen by the row kernels, per step
+ * Step j of an epoch:  ctr_epoch_tick(j) ; ctr_unique_segment(ids) ;
+ *   ctr_epoch_rows(apply=0, j)  -> gathered rows hold the state at the start of step j
+ *   forward / backward / ctr_segment_sum_rows ;  ctr_epoch_rows(apply=1, j) ;
+ *   after the last step (or to flush mid-epoch): ctr_epoch_sweep(upto, reset) ; ctr_epoch_reg_loss.
+ */
+int ctr_epoch_max_steps(void);
+int ctr_epoch_tick(float* state, float* hyper, int n_hyper, float* lr_table, int j, int is_adam,
+                   ctr_stream_t stream);
+int ctr_epoch_rows(int opt, int apply, float* var, float* slot0, float* slot1, uint8_t* last,
+                   const int32_t* uniq, const int32_t* n_uniq, const float* g_uniq, int64_t n_max, int K,
+                   const float* hyper, const float* lr_table, int j, double* ss, ctr_stream_t stream);
+/* ss_partials: device double[ctr_epoch_max_steps()][*n_partials_host] */
+int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* last, int64_t n_rows, int K,
+                    const float* hyper, const float* lr_table, int upto, int reset, double* ss_partials,
+                    int* n_partials_host, ctr_stream_t stream);
+/* reg[s] (+)= scale*(ss_rows[s] + sum_b ss_partials[s][b]) for s < upto; clears ss_rows[s] */
+int ctr_epoch_reg_loss(double* ss_rows, const double* ss_partials, int n_partials, int upto, float scale,
+                       float* reg, int accumulate, ctr_stream_t stream);
+
 /* ---- loss head -----------------------------------------------------------------------------------
  * y = ((bias + y_a) + y_b) + y_c (NULL terms skipped; DeepFM.py:172-175), pred = sigmoid(y)
  * (:176), loss_ce = sum(max(y,0) - y*t + log1p(exp(-|y|)))/B_total (:188), dy = (pred - t)/B_total,

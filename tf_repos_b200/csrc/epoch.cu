@@ -1,0 +1,403 @@
+// epoch.cu -- "exact-deferred" table update: bit-identical to sweeping every row every step
+// (optim.cu), at 1/P of the HBM traffic.
+//
+// Why this is legal: in TensorFlow's semantics a row that no gather touched at step
+// t still takes the optimizer step with g = l2*var.  That update is an element-wise recurrence on
+// (var, slot0, slot1) that depends on nothing but the row's own state and the scalar lr_t.  So it
+// can be *replayed later* -- exactly, in the same fp32 operation order -- the next time the row is
+// needed: when a batch gathers it (catch-up), or at the end of an epoch of P steps (epoch sweep),
+// where one pass over HBM applies P steps in registers.  A per-row byte `last` counts how many steps
+// of the current epoch are already applied to the stored state.
+//
+// Roofline: the plain sweep moves 24 B/element/step (HBM-bound, 13 ms at config 2); the epoch sweep
+// moves 24 B/element per P steps and executes P x ~36 instructions per element, i.e. it turns the
+// step from HBM-bound into FP32-issue-bound.
+//
+// Replaces the same reference lines as optim.cu: optimizer.minimize (DeepFM.py:204-213) with the
+// dense l2_loss gradient (DeepFM.py:189-190) [TF-sem].
+#include "optim_steps.cuh"
+
+namespace ctr {
+
+constexpr int EPOCH_MAX = 32;  // max steps per epoch (lr table / ss table size)
+
+__device__ __forceinline__ float sq4(const float4& x) {
+  return (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+}
+
+// Rows uniq[0..n_uniq): replay the untouched-row step for steps last[row]..j-1 so that the stored
+// state is the state at the START of step j; then (APPLY) take step j with the summed gradient.
+// ss[s] (double) accumulates sum(var^2) of the state each replayed/applied step started from.
+template <int OPT, int LPR, int VEC, bool APPLY>
+__global__ void __launch_bounds__(256)
+epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
+                  uint8_t* __restrict__ last, const int32_t* __restrict__ uniq,
+                  const int32_t* __restrict__ n_uniq, const float* __restrict__ g_uniq, int64_t n_max,
+                  const float* __restrict__ hyper, const float* __restrict__ lr_table, int j,
+                  double* __restrict__ ss) {
+  constexpr int K = 4 * LPR * VEC;
+  constexpr bool two = OptTraits<OPT>::slots == 2;
+  __shared__ double ss_blk[EPOCH_MAX];
+  if (threadIdx.x < EPOCH_MAX) ss_blk[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int c = threadIdx.x % LPR;
+  const bool active = u < n_max && u < n_uniq[0];
+  int64_t id = 0;
+  bool wrote = false;
+  if (active) {
+    Hyper h = load_hyper(hyper);
+    id = uniq[u];
+    const int l0 = last[id];
+    const int64_t row = id * K;
+    float4 x[VEC], a[VEC], b[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int64_t e = row + (c + v * LPR) * 4;
+      x[v] = *reinterpret_cast<const float4*>(var + e);
+      a[v] = *reinterpret_cast<const float4*>(slot0 + e);
+      b[v] = two ? *reinterpret_cast<const float4*>(slot1 + e) : f4_zero();
+    }
+    for (int s = l0; s < j; ++s) {
+      h.lr = lr_table[s];
+      float q = 0.f;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { q += sq4(x[v]); step_untouched4<OPT>(x[v], a[v], b[v], h); }
+      atomicAdd(&ss_blk[s], (double)q);
+    }
+    if (APPLY) {
+      h.lr = lr_table[j];
+      float q = 0.f;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        q += sq4(x[v]);
+        float4 g = *reinterpret_cast<const float4*>(g_uniq + u * K + (c + v * LPR) * 4);
+        g = make_float4(__fadd_rn(g.x, __fmul_rn(h.l2, x[v].x)), __fadd_rn(g.y, __fmul_rn(h.l2, x[v].y)),
+                        __fadd_rn(g.z, __fmul_rn(h.l2, x[v].z)), __fadd_rn(g.w, __fmul_rn(h.l2, x[v].w)));
+        step_sparse4<OPT>(x[v], a[v], b[v], g, h);
+      }
+      atomicAdd(&ss_blk[j], (double)q);
+    }
+    if (APPLY || l0 < j) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int64_t e = row + (c + v * LPR) * 4;
+        *reinterpret_cast<float4*>(var + e) = x[v];
+        *reinterpret_cast<float4*>(slot0 + e) = a[v];
+        if (two) *reinterpret_cast<float4*>(slot1 + e) = b[v];
+      }
+      wrote = true;
+    }
+  }
+  __syncthreads();  // every lane of a row has read `last` before lane 0 of the row rewrites it
+  if (wrote && c == 0) last[id] = (uint8_t)(APPLY ? j + 1 : j);
+  if (threadIdx.x < EPOCH_MAX && ss_blk[threadIdx.x] != 0.0) atomicAdd(&ss[threadIdx.x], ss_blk[threadIdx.x]);
+}
+
+// any K (incl. the scalar first-order table, K = 1): one thread per (row, k)
+template <int OPT, bool APPLY>
+__global__ void __launch_bounds__(256)
+epoch_rows_generic_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
+                          uint8_t* __restrict__ last, const int32_t* __restrict__ uniq,
+                          const int32_t* __restrict__ n_uniq, const float* __restrict__ g_uniq,
+                          int64_t n_max, int K, const float* __restrict__ hyper,
+                          const float* __restrict__ lr_table, int j, double* __restrict__ ss) {
+  constexpr bool two = OptTraits<OPT>::slots == 2;
+  __shared__ double ss_blk[EPOCH_MAX];
+  if (threadIdx.x < EPOCH_MAX) ss_blk[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t u = t / K;
+  const int k = (int)(t % K);
+  if (u < n_max && u < n_uniq[0]) {
+    Hyper h = load_hyper(hyper);
+    const int64_t id = uniq[u];
+    const int l0 = last[id];
+    const int64_t e = id * K + k;
+    float x = var[e], a = slot0[e], b = two ? slot1[e] : 0.f;
+    for (int s = l0; s < j; ++s) {
+      h.lr = lr_table[s];
+      atomicAdd(&ss_blk[s], (double)(x * x));
+      step_sparse<OPT>(x, a, b, __fmul_rn(h.l2, x), h);
+    }
+    if (APPLY) {
+      h.lr = lr_table[j];
+      atomicAdd(&ss_blk[j], (double)(x * x));
+      step_sparse<OPT>(x, a, b, __fadd_rn(g_uniq[u * K + k], __fmul_rn(h.l2, x)), h);
+    }
+    if (APPLY || l0 < j) {
+      var[e] = x; slot0[e] = a;
+      if (two) slot1[e] = b;
+    }
+  }
+  // the row's `last` byte is written after every k of the row has read it; the host wrapper only
+  // admits K that divide 256 here, so a row never straddles two CTAs
+  __syncthreads();
+  if (u < n_max && u < n_uniq[0] && k == 0) last[uniq[u]] = (uint8_t)(APPLY ? j + 1 : j);
+  if (threadIdx.x < EPOCH_MAX && ss_blk[threadIdx.x] != 0.0) atomicAdd(&ss[threadIdx.x], ss_blk[threadIdx.x]);
+}
+
+// All rows: replay steps last[row]..upto-1, reset `last` where it was non-zero (reset == true) or
+// raise it to `upto` (mid-epoch flush).  ss_partials[s][block] = sum(var^2) of the state step s
+// started from, over this block's elements.
+template <int OPT, int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+epoch_sweep_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
+                   uint8_t* __restrict__ last, int64_t n4, int K, const float* __restrict__ hyper,
+                   const float* __restrict__ lr_table, int upto, int reset,
+                   double* __restrict__ ss_partials) {
+  constexpr bool two = OptTraits<OPT>::slots == 2;
+  __shared__ float lr_s[EPOCH_MAX];
+  __shared__ double ss_blk[EPOCH_MAX];
+  if (threadIdx.x < EPOCH_MAX) {
+    lr_s[threadIdx.x] = (threadIdx.x < upto) ? lr_table[threadIdx.x] : 0.f;
+    ss_blk[threadIdx.x] = 0.0;
+  }
+  __syncthreads();
+  Hyper h = load_hyper(hyper);
+  float4* v4 = reinterpret_cast<float4*>(var);
+  float4* a4 = reinterpret_cast<float4*>(slot0);
+  float4* b4 = reinterpret_cast<float4*>(slot1);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int f4_per_row = K >> 2;  // K % 4 == 0 here
+  const bool pow2 = (f4_per_row & (f4_per_row - 1)) == 0;
+  const int sh = 31 - __clz(f4_per_row);
+  auto row_of = [&](int64_t i) { return pow2 ? (i >> sh) : (i / f4_per_row); };
+  auto row_head = [&](int64_t i) { return pow2 ? ((i & (f4_per_row - 1)) == 0) : ((i % f4_per_row) == 0); };
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += UNROLL * stride) {
+    float4 x[UNROLL], a[UNROLL], b[UNROLL];
+    int l0[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) {
+        x[u] = ld_stream4(v4 + i);
+        a[u] = ld_stream4(a4 + i);
+        b[u] = two ? ld_stream4(b4 + i) : f4_zero();
+        l0[u] = last[row_of(i)];
+      } else {
+        l0[u] = upto;
+      }
+    }
+    // common case: every lane replays steps 0..upto-1 (rows not gathered this epoch)
+#pragma unroll 1
+    for (int s = 0; s < upto; ++s) {
+      h.lr = lr_s[s];
+      float q = 0.f;
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (s >= l0[u]) {
+          q += sq4(x[u]);
+          step_untouched4<OPT>(x[u], a[u], b[u], h);
+        }
+      }
+      q = warp_sum(q);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&ss_blk[s], (double)q);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4 && l0[u] < upto) {
+        st_stream4(v4 + i, x[u]);
+        st_stream4(a4 + i, a[u]);
+        if (two) st_stream4(b4 + i, b[u]);
+      }
+      if (i < n4 && row_head(i)) {
+        const uint8_t nl = reset ? (uint8_t)0 : (uint8_t)(l0[u] < upto ? upto : l0[u]);
+        if ((uint8_t)l0[u] != nl) last[row_of(i)] = nl;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < upto) ss_partials[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = ss_blk[threadIdx.x];
+}
+
+// scalar table / K % 4 != 0: one thread per element
+template <int OPT>
+__global__ void __launch_bounds__(256)
+epoch_sweep_generic_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
+                           uint8_t* __restrict__ last, int64_t n_elem, int K,
+                           const float* __restrict__ hyper, const float* __restrict__ lr_table, int upto,
+                           int reset, double* __restrict__ ss_partials) {
+  constexpr bool two = OptTraits<OPT>::slots == 2;
+  __shared__ float lr_s[EPOCH_MAX];
+  __shared__ double ss_blk[EPOCH_MAX];
+  if (threadIdx.x < EPOCH_MAX) {
+    lr_s[threadIdx.x] = (threadIdx.x < upto) ? lr_table[threadIdx.x] : 0.f;
+    ss_blk[threadIdx.x] = 0.0;
+  }
+  __syncthreads();
+  Hyper h = load_hyper(hyper);
+  float ssq[EPOCH_MAX];
+#pragma unroll
+  for (int s = 0; s < EPOCH_MAX; ++s) ssq[s] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem; e += stride) {
+    const int64_t row = e / K;
+    const int l0 = last[row];
+    if (l0 < upto) {
+      float x = var[e], a = slot0[e], b = two ? slot1[e] : 0.f;
+#pragma unroll 1
+      for (int s = l0; s < upto; ++s) {
+        h.lr = lr_s[s];
+        ssq[s] += x * x;
+        step_sparse<OPT>(x, a, b, __fmul_rn(h.l2, x), h);
+      }
+      var[e] = x; slot0[e] = a;
+      if (two) slot1[e] = b;
+    }
+  }
+#pragma unroll 1
+  for (int s = 0; s < upto; ++s) {
+    float q = warp_sum(ssq[s]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&ss_blk[s], (double)q);
+  }
+  __syncthreads();
+  if (threadIdx.x < upto) ss_partials[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = ss_blk[threadIdx.x];
+}
+
+// `last` of the generic sweep is updated by a separate pass (all k of a row must have read it first)
+__global__ void epoch_last_kernel(uint8_t* __restrict__ last, int64_t n_rows, int upto, int reset) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+    const uint8_t l0 = last[r];
+    const uint8_t nl = reset ? (uint8_t)0 : (uint8_t)(l0 < upto ? upto : l0);
+    if (l0 != nl) last[r] = nl;
+  }
+}
+
+// lr_table[j] = this step's lr_t; Adam: also refresh hyper[8*r] and advance the beta powers
+__global__ void epoch_tick_kernel(float* __restrict__ state, float* __restrict__ hyper, int n_hyper,
+                                  float* __restrict__ lr_table, int j, int is_adam) {
+  float lr_t = state[2];
+  if (is_adam) {
+    const float b1p = state[0], b2p = state[1];
+    lr_t = __fdiv_rn(__fmul_rn(state[2], __fsqrt_rn(__fsub_rn(1.f, b2p))), __fsub_rn(1.f, b1p));
+    for (int r = 0; r < n_hyper; ++r) hyper[8 * r] = lr_t;
+    state[0] = __fmul_rn(b1p, hyper[1]);
+    state[1] = __fmul_rn(b2p, hyper[2]);
+  }
+  state[3] = state[3] + 1.f;
+  lr_table[j] = lr_t;
+}
+
+// reg[s] = scale * (ss_rows[s] + sum_b partials[s][b]), s < upto; clears ss_rows for the next epoch
+__global__ void epoch_reg_kernel(double* __restrict__ ss_rows, const double* __restrict__ partials,
+                                 int n_partials, int upto, float scale, float* __restrict__ reg,
+                                 int accumulate) {
+  const int s = blockIdx.x;
+  __shared__ double sh[256];
+  double t = 0.0;
+  for (int b = threadIdx.x; b < n_partials; b += 256) t += partials[(int64_t)s * n_partials + b];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && s < upto) {
+    const float r = (float)((double)scale * (sh[0] + ss_rows[s]));
+    reg[s] = accumulate ? reg[s] + r : r;
+    ss_rows[s] = 0.0;
+  }
+}
+
+}  // namespace ctr
+
+using namespace ctr;
+
+extern "C" {
+
+int ctr_epoch_max_steps(void) { return EPOCH_MAX; }
+
+int ctr_epoch_tick(float* state, float* hyper, int n_hyper, float* lr_table, int j, int is_adam,
+                   ctr_stream_t stream) {
+  CTR_REQUIRE(state && hyper && lr_table && n_hyper >= 1 && j >= 0 && j < EPOCH_MAX, CTR_ERR_INVALID_ARG,
+              "ctr_epoch_tick: bad args (j=%d)", j);
+  epoch_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(state, hyper, n_hyper, lr_table, j, is_adam);
+  CTR_LAUNCHED("ctr_epoch_tick");
+  return CTR_OK;
+}
+
+int ctr_epoch_rows(int opt, int apply, float* var, float* slot0, float* slot1, uint8_t* last,
+                   const int32_t* uniq, const int32_t* n_uniq, const float* g_uniq, int64_t n_max, int K,
+                   const float* hyper, const float* lr_table, int j, double* ss, ctr_stream_t stream) {
+  CTR_REQUIRE(n_max >= 0 && K > 0 && j >= 0 && j < EPOCH_MAX, CTR_ERR_INVALID_ARG,
+              "ctr_epoch_rows: bad n_max/K/j");
+  if (n_max == 0) return CTR_OK;
+  CTR_REQUIRE(var && slot0 && last && uniq && n_uniq && hyper && lr_table && ss, CTR_ERR_INVALID_ARG,
+              "ctr_epoch_rows: null buffer");
+  CTR_REQUIRE(!apply || g_uniq, CTR_ERR_INVALID_ARG, "ctr_epoch_rows: g_uniq required when apply != 0");
+  CTR_REQUIRE(n_slots_of(opt) == 1 || slot1, CTR_ERR_INVALID_ARG, "ctr_epoch_rows: slot1 required");
+  // generic path: a row's K threads must sit in one CTA (they synchronise on the row's `last` byte)
+  CTR_REQUIRE(K % 4 == 0 || 256 % K == 0, CTR_ERR_UNSUPPORTED,
+              "ctr_epoch_rows: K=%d must be a multiple of 4 or divide 256", K);
+  cudaStream_t st = as_stream(stream);
+#define ER_K(OPT, AP, KK, LPR, VEC)                                                                  \
+  case KK:                                                                                           \
+    epoch_rows_kernel<OPT, LPR, VEC, AP><<<(unsigned)ceil_div64(n_max * LPR, 256), 256, 0, st>>>(    \
+        var, slot0, slot1, last, uniq, n_uniq, g_uniq, n_max, hyper, lr_table, j, ss);               \
+    break;
+#define ER_AP(OPT, AP)                                                                               \
+  switch (K) {                                                                                       \
+    ER_K(OPT, AP, 4, 1, 1) ER_K(OPT, AP, 8, 2, 1) ER_K(OPT, AP, 16, 4, 1) ER_K(OPT, AP, 32, 8, 1)    \
+    ER_K(OPT, AP, 64, 16, 1) ER_K(OPT, AP, 128, 32, 1) ER_K(OPT, AP, 256, 32, 2)                     \
+    default:                                                                                         \
+      epoch_rows_generic_kernel<OPT, AP><<<(unsigned)ceil_div64(n_max * K, 256), 256, 0, st>>>(      \
+          var, slot0, slot1, last, uniq, n_uniq, g_uniq, n_max, K, hyper, lr_table, j, ss);          \
+  }
+#define ER_CALL(OPT)                     \
+  if (apply) { ER_AP(OPT, true) } else { ER_AP(OPT, false) }
+  CTR_OPT_SWITCH(opt, ER_CALL)
+#undef ER_CALL
+#undef ER_AP
+#undef ER_K
+  CTR_LAUNCHED("ctr_epoch_rows");
+  return CTR_OK;
+}
+
+int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* last, int64_t n_rows, int K,
+                    const float* hyper, const float* lr_table, int upto, int reset, double* ss_partials,
+                    int* n_partials_host, ctr_stream_t stream) {
+  CTR_REQUIRE(n_rows >= 0 && K > 0 && upto >= 0 && upto <= EPOCH_MAX, CTR_ERR_INVALID_ARG,
+              "ctr_epoch_sweep: bad n_rows/K/upto");
+  const int grid = sm_count() * 3;
+  if (n_partials_host) *n_partials_host = grid;
+  if (n_rows == 0 || upto == 0) return CTR_OK;
+  CTR_REQUIRE(var && slot0 && last && hyper && lr_table && ss_partials, CTR_ERR_INVALID_ARG,
+              "ctr_epoch_sweep: null buffer");
+  CTR_REQUIRE(n_slots_of(opt) == 1 || slot1, CTR_ERR_INVALID_ARG, "ctr_epoch_sweep: slot1 required");
+  cudaStream_t st = as_stream(stream);
+  const int64_t n_elem = n_rows * K;
+  if (K % 4 == 0) {
+#define ES_CALL(OPT)                                                                                 \
+  epoch_sweep_kernel<OPT, 4, 3><<<grid, 256, 0, st>>>(var, slot0, slot1, last, n_elem / 4, K, hyper,  \
+                                                      lr_table, upto, reset, ss_partials);
+    CTR_OPT_SWITCH(opt, ES_CALL)
+#undef ES_CALL
+    CTR_LAUNCHED("ctr_epoch_sweep");
+  } else {
+#define ESG_CALL(OPT)                                                                                \
+  epoch_sweep_generic_kernel<OPT><<<grid, 256, 0, st>>>(var, slot0, slot1, last, n_elem, K, hyper,   \
+                                                        lr_table, upto, reset, ss_partials);
+    CTR_OPT_SWITCH(opt, ESG_CALL)
+#undef ESG_CALL
+    CTR_LAUNCHED("ctr_epoch_sweep(generic)");
+    epoch_last_kernel<<<grid, 256, 0, st>>>(last, n_rows, upto, reset);
+    CTR_LAUNCHED("ctr_epoch_sweep(last)");
+  }
+  return CTR_OK;
+}
+
+int ctr_epoch_reg_loss(double* ss_rows, const double* ss_partials, int n_partials, int upto, float scale,
+                       float* reg, int accumulate, ctr_stream_t stream) {
+  CTR_REQUIRE(ss_rows && ss_partials && reg && n_partials >= 0 && upto >= 0 && upto <= EPOCH_MAX,
+              CTR_ERR_INVALID_ARG, "ctr_epoch_reg_loss: bad args");
+  if (upto == 0) return CTR_OK;
+  epoch_reg_kernel<<<upto, 256, 0, as_stream(stream)>>>(ss_rows, ss_partials, n_partials, upto, scale, reg,
+                                                        accumulate);
+  CTR_LAUNCHED("ctr_epoch_reg_loss");
+  return CTR_OK;
+}
+
+}  // extern "C"

@@ -10,72 +10,11 @@
 // updates EVERY row each step: rows gathered this step get g = segment_sum + l2*var, all others
 // g = l2*var.  `ctr_opt_dense_sweep` is that full-table pass: a pure HBM stream
 // (read var,slot0,slot1; write var,slot0,slot1) -- 24 B/element for Adam.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "optim_steps.cuh"
 
 namespace ctr {
-
-// hyper[] layout (device): {lr_t, beta1, beta2, eps, l2_reg, aux0, aux1, aux2}
-struct Hyper {
-  float lr, b1, b2, eps, l2, a0, a1, a2;
-};
-__device__ __forceinline__ Hyper load_hyper(const float* __restrict__ h) {
-  Hyper r;
-  r.lr = h[0]; r.b1 = h[1]; r.b2 = h[2]; r.eps = h[3]; r.l2 = h[4]; r.a0 = h[5]; r.a1 = h[6]; r.a2 = h[7];
-  return r;
-}
-
-// ---- element-wise update rules -------------------------------------------------------------------
-// sparse flavour = what the *sparse* apply of each TF optimizer computes for a row with summed
-// gradient g (also used by the dense sweep with g = l2*var).
-template <int OPT>
-__device__ __forceinline__ void step_sparse(float& var, float& s0, float& s1, float g, const Hyper& h) {
-  if (OPT == CTR_OPT_ADAM) {
-    const float omb1 = __fsub_rn(1.f, h.b1), omb2 = __fsub_rn(1.f, h.b2);
-    s0 = __fadd_rn(__fmul_rn(s0, h.b1), __fmul_rn(g, omb1));
-    s1 = __fadd_rn(__fmul_rn(s1, h.b2), __fmul_rn(__fmul_rn(g, g), omb2));
-    var = __fsub_rn(var, __fdiv_rn(__fmul_rn(h.lr, s0), __fadd_rn(__fsqrt_rn(s1), h.eps)));
-  } else if (OPT == CTR_OPT_ADAGRAD) {
-    s0 = __fadd_rn(s0, __fmul_rn(g, g));
-    var = __fsub_rn(var, __fmul_rn(__fmul_rn(h.lr, g), __fdiv_rn(1.f, __fsqrt_rn(s0))));
-  } else if (OPT == CTR_OPT_MOMENTUM) {
-    s0 = __fadd_rn(__fmul_rn(s0, h.a0), g);
-    var = __fsub_rn(var, __fmul_rn(s0, h.lr));
-  } else {  // FTRL (lr_power aux0, l1 aux1, l2 aux2); slot0 = accum, slot1 = linear
-    const float new_acc = __fadd_rn(s0, __fmul_rn(g, g));
-    float pn, po;
-    if (h.a0 == -0.5f) { pn = __fsqrt_rn(new_acc); po = __fsqrt_rn(s0); }
-    else { pn = powf(new_acc, -h.a0); po = powf(s0, -h.a0); }
-    s1 = __fadd_rn(s1, __fsub_rn(g, __fmul_rn(__fdiv_rn(__fsub_rn(pn, po), h.lr), var)));
-    const float sgn = (s1 > 0.f) ? 1.f : ((s1 < 0.f) ? -1.f : 0.f);
-    const float xx = __fsub_rn(__fmul_rn(h.a1, sgn), s1);
-    const float yy = __fadd_rn(__fdiv_rn(pn, h.lr), __fmul_rn(2.f, h.a2));
-    var = (fabsf(s1) > h.a1) ? __fdiv_rn(xx, yy) : 0.f;
-    s0 = new_acc;
-  }
-}
-
-// dense flavour = TF's fused Apply* kernels for ordinary variables
-template <int OPT>
-__device__ __forceinline__ void step_dense(float& var, float& s0, float& s1, float g, const Hyper& h) {
-  if (OPT == CTR_OPT_ADAM) {
-    // m += (g-m)*(1-b1); v += (g*g-v)*(1-b2); var -= (m*alpha)/(sqrt(v)+eps)
-    s0 = __fadd_rn(s0, __fmul_rn(__fsub_rn(g, s0), __fsub_rn(1.f, h.b1)));
-    s1 = __fadd_rn(s1, __fmul_rn(__fsub_rn(__fmul_rn(g, g), s1), __fsub_rn(1.f, h.b2)));
-    var = __fsub_rn(var, __fdiv_rn(__fmul_rn(s0, h.lr), __fadd_rn(__fsqrt_rn(s1), h.eps)));
-  } else {
-    step_sparse<OPT>(var, s0, s1, g, h);  // identical arithmetic for adagrad/momentum/ftrl
-  }
-}
-
-template <int OPT>
-__device__ __forceinline__ void step_sparse4(float4& var, float4& s0, float4& s1, float4 g, const Hyper& h) {
-  step_sparse<OPT>(var.x, s0.x, s1.x, g.x, h);
-  step_sparse<OPT>(var.y, s0.y, s1.y, g.y, h);
-  step_sparse<OPT>(var.z, s0.z, s1.z, g.z, h);
-  step_sparse<OPT>(var.w, s0.w, s1.w, g.w, h);
-}
-
-template <int OPT> struct OptTraits { static constexpr int slots = (OPT == CTR_OPT_ADAM || OPT == CTR_OPT_FTRL) ? 2 : 1; };
 
 // ---- sparse rows --------------------------------------------------------------------------------
 // LPR lanes per row.  g = g_uniq + l2*var (the l2 term is a separate IndexedSlices entry in TF,
@@ -159,10 +98,12 @@ opt_patch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float*
 
 // ---- dense sweep (the dominant kernel of an exact-TF step: pure HBM stream) -----------------------
 constexpr int SWEEP_THREADS = 256;
-constexpr int SWEEP_UNROLL = 4;
 
-template <int OPT>
-__global__ void __launch_bounds__(SWEEP_THREADS)
+// UNROLL float4 triples in flight per thread; MINB = resident CTAs per SM the register budget is
+// squeezed for (tuned on B200, see profiles/): the kernel is a pure stream, so what matters is bytes
+// in flight per SM = MINB * 256 threads * UNROLL * 48 B.
+template <int OPT, int SWEEP_UNROLL, int MINB>
+__global__ void __launch_bounds__(SWEEP_THREADS, MINB)
 opt_dense_sweep_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
                        int64_t n4, int64_t n_elem, const float* __restrict__ hyper,
                        float* __restrict__ sumsq_partials) {
@@ -305,19 +246,6 @@ static int reduce_grid(int64_t n) {
 
 using namespace ctr;
 
-#define OPT_SWITCH(opt, CALL)                                            \
-  switch (opt) {                                                         \
-    case CTR_OPT_ADAM: { CALL(CTR_OPT_ADAM) } break;                     \
-    case CTR_OPT_ADAGRAD: { CALL(CTR_OPT_ADAGRAD) } break;               \
-    case CTR_OPT_MOMENTUM: { CALL(CTR_OPT_MOMENTUM) } break;             \
-    case CTR_OPT_FTRL: { CALL(CTR_OPT_FTRL) } break;                     \
-    default:                                                             \
-      set_error("unknown optimizer %d", opt);                            \
-      return CTR_ERR_INVALID_ARG;                                        \
-  }
-
-static int n_slots_of(int opt) { return (opt == CTR_OPT_ADAM || opt == CTR_OPT_FTRL) ? 2 : 1; }
-
 extern "C" {
 
 int ctr_opt_sparse_rows(int opt, float* var, float* slot0, float* slot1, const int32_t* uniq,
@@ -342,7 +270,7 @@ int ctr_opt_sparse_rows(int opt, float* var, float* slot0, float* slot1, const i
       opt_sparse_generic_kernel<OPT><<<(unsigned)ceil_div64(n_max * K, 256), 256, 0, st>>>(       \
           var, slot0, slot1, uniq, n_uniq, g_uniq, n_max, K, hyper, stage);                       \
   }
-  OPT_SWITCH(opt, ROWS_CALL)
+  CTR_OPT_SWITCH(opt, ROWS_CALL)
 #undef ROWS_CALL
 #undef ROWS_K
   CTR_LAUNCHED("ctr_opt_sparse_rows");
@@ -353,8 +281,16 @@ int ctr_opt_dense_sweep(int opt, float* var, float* slot0, float* slot1, int64_t
                         const float* hyper, float* sumsq_partials, int* n_partials_host,
                         ctr_stream_t stream) {
   CTR_REQUIRE(n_elem >= 0, CTR_ERR_INVALID_ARG, "ctr_opt_dense_sweep: n_elem < 0");
-  const int grid = sm_count() * 8;
-  if (n_partials_host) *n_partials_host = grid;
+  // tuning hook (tools/tune_sweep.py): CTR_SWEEP_CFG = 0..3 selects (unroll, CTAs/SM)
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char* e = getenv("CTR_SWEEP_CFG");
+    cfg = e ? atoi(e) : 0;
+    if (cfg < 0 || cfg > 3) cfg = 0;
+  }
+  static const int kBlocksPerSm[4] = {2, 4, 3, 6};
+  const int grid = sm_count() * kBlocksPerSm[cfg];
+  if (n_partials_host) *n_partials_host = sm_count() * 8;
   if (n_elem == 0) return CTR_OK;
   CTR_REQUIRE(var && slot0 && hyper, CTR_ERR_INVALID_ARG, "ctr_opt_dense_sweep: null buffer");
   CTR_REQUIRE(n_slots_of(opt) == 1 || slot1, CTR_ERR_INVALID_ARG, "ctr_opt_dense_sweep: slot1 required");
@@ -362,11 +298,19 @@ int ctr_opt_dense_sweep(int opt, float* var, float* slot0, float* slot1, int64_t
               CTR_ERR_INVALID_ARG, "ctr_opt_dense_sweep: tensors must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   const int64_t n4 = n_elem / 4;
-#define SWEEP_CALL(OPT)                                                                          \
-  opt_dense_sweep_kernel<OPT><<<grid, SWEEP_THREADS, 0, st>>>(var, slot0, slot1, n4, n_elem, hyper, \
-                                                              sumsq_partials);
-  OPT_SWITCH(opt, SWEEP_CALL)
+#define SWEEP_LAUNCH(OPT, U, MB)                                                                   \
+  opt_dense_sweep_kernel<OPT, U, MB><<<grid, SWEEP_THREADS, 0, st>>>(var, slot0, slot1, n4, n_elem, \
+                                                                     hyper, sumsq_partials)
+#define SWEEP_CALL(OPT)                                   \
+  switch (cfg) {                                          \
+    case 1: SWEEP_LAUNCH(OPT, 2, 4); break;               \
+    case 2: SWEEP_LAUNCH(OPT, 4, 3); break;               \
+    case 3: SWEEP_LAUNCH(OPT, 1, 6); break;               \
+    default: SWEEP_LAUNCH(OPT, 4, 2); break;              \
+  }
+  CTR_OPT_SWITCH(opt, SWEEP_CALL)
 #undef SWEEP_CALL
+#undef SWEEP_LAUNCH
   CTR_LAUNCHED("ctr_opt_dense_sweep");
   return CTR_OK;
 }
@@ -395,7 +339,7 @@ int ctr_opt_dense_grad(int opt, float* var, float* slot0, float* slot1, const fl
   int64_t b = ceil_div64(n_elem, 256);
   const int grid = (int)(b > (int64_t)sm_count() * 8 ? (int64_t)sm_count() * 8 : b);
 #define DG_CALL(OPT) opt_dense_grad_kernel<OPT><<<grid, 256, 0, st>>>(var, slot0, slot1, grad, n_elem, hyper);
-  OPT_SWITCH(opt, DG_CALL)
+  CTR_OPT_SWITCH(opt, DG_CALL)
 #undef DG_CALL
   CTR_LAUNCHED("ctr_opt_dense_grad");
   return CTR_OK;

@@ -5,8 +5,9 @@
 //
 // Algorithm: stable LSD radix sort of (id, position) -- ceil(bits/10) passes of <=10-bit digits
 // (3 passes cover N <= 2^30, i.e. the 1e9-row table of config 5) -- then run-length encoding.
-// Every pass is three small kernels (tile histogram -> exclusive scan -> stable scatter), no
-// inter-CTA spinning, so the whole thing is graph-capturable and cannot hang.
+// Every pass is three small kernels (tile histogram + digit totals -> per-digit column scan over
+// the tiles -> stable scatter), linear in n, no inter-CTA spinning, so the whole thing is
+// graph-capturable and cannot hang.
 // n = B*F = 319 488 at config 2: all buffers (2.5 MB) stay L2-resident; the cost is launch
 // latency, not bandwidth.
 #include "common.cuh"
@@ -27,7 +28,7 @@ __device__ __forceinline__ uint32_t sanitize_key(int32_t id, int64_t N) {
 
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int64_t N, int shift, int nbins,
-                  int32_t* __restrict__ hist, int n_tiles) {
+                  int32_t* __restrict__ hist, int32_t* __restrict__ totals) {
   __shared__ int32_t sh[MAX_BINS];
   for (int d = threadIdx.x; d < nbins; d += SORT_THREADS) sh[d] = 0;
   __syncthreads();
@@ -39,41 +40,48 @@ radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int64_t N, int sh
     if (i < n) atomicAdd(&sh[(sanitize_key(keys[i], N) >> shift) & mask], 1);
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < nbins; d += SORT_THREADS) hist[(int64_t)d * n_tiles + blockIdx.x] = sh[d];
+  // tile-major [tile][digit] (coalesced here, in the column scan and in the scatter) + digit totals
+  for (int d = threadIdx.x; d < nbins; d += SORT_THREADS) {
+    const int32_t c = sh[d];
+    hist[(int64_t)blockIdx.x * nbins + d] = c;
+    if (c) atomicAdd(&totals[d], c);
+  }
 }
 
-// in-place exclusive scan of `len` int32 by one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) scan_exclusive_kernel(int32_t* __restrict__ data, int len) {
-  __shared__ int32_t warp_tot[32];
-  const int tid = threadIdx.x;
-  const int chunk = (len + 1023) / 1024;
-  const int lo = min(len, tid * chunk), hi = min(len, lo + chunk);
+// hist[tile][digit] -> exclusive prefix over tiles, per digit column, in place.
+// One CTA = 32 columns x 32 row segments: thread (seg, col) sums its segment (warp = 32 consecutive
+// columns of one segment => 128 B coalesced rows), a 32-step scan over the segments in shared
+// memory, then the segment is rewritten with its running prefix.  Linear in n_tiles.
+__global__ void __launch_bounds__(1024)
+radix_colscan_kernel(int32_t* __restrict__ hist, int nbins, int n_tiles) {
+  __shared__ int32_t seg_sum[32][33];
+  const int col_l = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + col_l;
+  const int rows_per = (n_tiles + 31) / 32;
+  const int r0 = min(n_tiles, seg * rows_per), r1 = min(n_tiles, r0 + rows_per);
   int32_t sum = 0;
-  for (int i = lo; i < hi; ++i) sum += data[i];
-  // block exclusive scan of `sum`
-  int32_t incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int32_t t = __shfl_up_sync(FULL_MASK, incl, o);
-    if ((tid & 31) >= o) incl += t;
-  }
-  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+  if (col < nbins)
+    for (int r = r0; r < r1; ++r) sum += hist[(int64_t)r * nbins + col];
+  seg_sum[seg][col_l] = sum;
   __syncthreads();
-  if (tid < 32) {
-    int32_t w = warp_tot[tid], wi = w;
+  if (seg == 0) {
+    int32_t run = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int32_t t = __shfl_up_sync(FULL_MASK, wi, o);
-      if (tid >= o) wi += t;
+    for (int sgm = 0; sgm < 32; ++sgm) {
+      const int32_t v = seg_sum[sgm][col_l];
+      seg_sum[sgm][col_l] = run;
+      run += v;
     }
-    warp_tot[tid] = wi - w;
   }
   __syncthreads();
-  int32_t run = warp_tot[tid >> 5] + incl - sum;
-  for (int i = lo; i < hi; ++i) {
-    int32_t v = data[i];
-    data[i] = run;
-    run += v;
+  if (col < nbins) {
+    int32_t run = seg_sum[seg][col_l];
+    for (int r = r0; r < r1; ++r) {
+      const int64_t i = (int64_t)r * nbins + col;
+      const int32_t v = hist[i];
+      hist[i] = run;
+      run += v;
+    }
   }
 }
 
@@ -81,11 +89,32 @@ __global__ void __launch_bounds__(1024) scan_exclusive_kernel(int32_t* __restric
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                      int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, int64_t n,
-                     int64_t N, int shift, int nbins, const int32_t* __restrict__ offsets,
-                     int n_tiles) {
+                     int64_t N, int shift, int nbins, const int32_t* __restrict__ tile_prefix,
+                     const int32_t* __restrict__ totals) {
   extern __shared__ int32_t warp_hist[];  // [SORT_WARPS][nbins]
+  __shared__ int32_t digit_base[MAX_BINS];  // exclusive scan of the digit totals
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   for (int d = tid; d < SORT_WARPS * nbins; d += SORT_THREADS) warp_hist[d] = 0;
+  for (int d = tid; d < nbins; d += SORT_THREADS) digit_base[d] = totals[d];
+  __syncthreads();
+  if (w == 0) {  // one warp: lane-contiguous chunks, then a shuffle scan over the 32 chunk sums
+    const int per = (nbins + 31) / 32;
+    const int lo = min(nbins, lane * per), hi = min(nbins, lo + per);
+    int32_t sum = 0;
+    for (int d = lo; d < hi; ++d) sum += digit_base[d];
+    int32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t t = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int32_t run = incl - sum;
+    for (int d = lo; d < hi; ++d) {
+      const int32_t v = digit_base[d];
+      digit_base[d] = run;
+      run += v;
+    }
+  }
   __syncthreads();
   const uint32_t mask = (uint32_t)nbins - 1u;
   const int64_t wstart = (int64_t)blockIdx.x * SORT_TILE + (int64_t)w * (SORT_ITEMS * 32);
@@ -114,7 +143,7 @@ radix_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restr
   __syncthreads();
   // per digit: exclusive prefix over the warps of this tile + the tile's global offset
   for (int d = tid; d < nbins; d += SORT_THREADS) {
-    int32_t run = offsets[(int64_t)d * n_tiles + blockIdx.x];
+    int32_t run = digit_base[d] + tile_prefix[(int64_t)blockIdx.x * nbins + d];
 #pragma unroll
     for (int ww = 0; ww < SORT_WARPS; ++ww) {
       int32_t cnt = warp_hist[ww * nbins + d];
@@ -154,17 +183,25 @@ heads_count_kernel(const int32_t* __restrict__ keys, int64_t n, int32_t* __restr
 #pragma unroll
     for (int ww = 0; ww < SORT_WARPS; ++ww) t += wsum[ww];
     tile_counts[blockIdx.x] = t;
-    if (blockIdx.x == 0) { tile_counts[n_tiles] = 0; long_list[0] = 0; }
+    if (blockIdx.x == 0) long_list[0] = 0;
   }
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
 heads_emit_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ perm, int64_t n,
-                  const int32_t* __restrict__ tile_offsets, int32_t* __restrict__ uniq,
+                  const int32_t* __restrict__ tile_counts, int32_t* __restrict__ uniq,
                   int32_t* __restrict__ seg_offsets, int32_t* __restrict__ inverse,
                   int32_t* __restrict__ n_uniq) {
   __shared__ int32_t warp_tot[SORT_WARPS];
+  __shared__ int32_t tile_off_s[SORT_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  {  // runs that start in earlier tiles
+    int32_t c = 0;
+    for (int t = tid; t < (int)blockIdx.x; t += SORT_THREADS) c += tile_counts[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+    if (lane == 0) tile_off_s[w] = c;
+  }
   // blocked arrangement: thread t owns items [t*ITEMS, (t+1)*ITEMS) of the tile
   const int64_t start = (int64_t)blockIdx.x * SORT_TILE + (int64_t)tid * SORT_ITEMS;
   int32_t k[SORT_ITEMS];
@@ -190,7 +227,10 @@ heads_emit_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ 
   int32_t wbase = 0;
 #pragma unroll
   for (int ww = 0; ww < SORT_WARPS; ++ww) wbase += (ww < w) ? warp_tot[ww] : 0;
-  int32_t u = tile_offsets[blockIdx.x] + wbase + incl - cnt - 1;  // index of the run before my first item
+  int32_t tile_off = 0;
+#pragma unroll
+  for (int ww = 0; ww < SORT_WARPS; ++ww) tile_off += tile_off_s[ww];
+  int32_t u = tile_off + wbase + incl - cnt - 1;  // index of the run before my first item
 #pragma unroll
   for (int r = 0; r < SORT_ITEMS; ++r) {
     const int64_t i = start + r;
@@ -226,7 +266,7 @@ __global__ void empty_unique_kernel(int32_t* n_uniq, int32_t* seg_offsets, int32
 
 struct SortPlan {
   int bits, passes, digit_bits, n_tiles;
-  size_t off_keys_a, off_keys_b, off_vals_a, off_hist, off_tiles, total;
+  size_t off_keys_a, off_keys_b, off_vals_a, off_hist, off_tiles, off_totals, total;
 };
 
 static SortPlan make_plan(int64_t n, int64_t N) {
@@ -244,6 +284,7 @@ static SortPlan make_plan(int64_t n, int64_t N) {
   p.off_vals_a = o; o = align(o + (size_t)n * 4);
   p.off_hist = o;   o = align(o + ((size_t)MAX_BINS * p.n_tiles + 1) * 4);
   p.off_tiles = o;  o = align(o + ((size_t)p.n_tiles + 1) * 4);
+  p.off_totals = o; o = align(o + (size_t)4 * MAX_BINS * 4);  // one totals row per pass (<= 4 passes)
   p.total = o;
   return p;
 }
@@ -284,8 +325,13 @@ int ctr_unique_segment(const int32_t* ids, int64_t n, int64_t N, int32_t* perm, 
   int32_t* vals_a = reinterpret_cast<int32_t*>(base + p.off_vals_a);
   int32_t* hist = reinterpret_cast<int32_t*>(base + p.off_hist);
   int32_t* tiles = reinterpret_cast<int32_t*>(base + p.off_tiles);
+  int32_t* totals = reinterpret_cast<int32_t*>(base + p.off_totals);
   const int nbins = 1 << p.digit_bits;
-  static_assert(SORT_WARPS * MAX_BINS * 4 <= 48 * 1024, "scatter smem must fit the default carve-out");
+  if (cudaMemsetAsync(totals, 0, (size_t)4 * MAX_BINS * 4, st) != cudaSuccess) {
+    set_error("ctr_unique_segment: memset failed");
+    return CTR_ERR_CUDA;
+  }
+  static_assert((SORT_WARPS + 1) * MAX_BINS * 4 <= 48 * 1024, "scatter smem must fit the default carve-out");
   const int32_t* kin = ids;
   const int32_t* vin = nullptr;  // implicit iota
   for (int pass = 0; pass < p.passes; ++pass) {
@@ -293,20 +339,19 @@ int ctr_unique_segment(const int32_t* ids, int64_t n, int64_t N, int32_t* perm, 
     int32_t* kout = keys_ab[pass & 1];
     // the last pass must land the positions in `perm`
     int32_t* vout = (((p.passes - 1 - pass) & 1) == 0) ? perm : vals_a;
-    radix_hist_kernel<<<p.n_tiles, SORT_THREADS, 0, st>>>(kin, n, N, shift, nbins, hist, p.n_tiles);
+    int32_t* tot = totals + pass * MAX_BINS;
+    radix_hist_kernel<<<p.n_tiles, SORT_THREADS, 0, st>>>(kin, n, N, shift, nbins, hist, tot);
     CTR_LAUNCHED("radix_hist");
-    scan_exclusive_kernel<<<1, 1024, 0, st>>>(hist, nbins * p.n_tiles);
-    CTR_LAUNCHED("radix_scan");
+    radix_colscan_kernel<<<(nbins + 31) / 32, 1024, 0, st>>>(hist, nbins, p.n_tiles);
+    CTR_LAUNCHED("radix_colscan");
     radix_scatter_kernel<<<p.n_tiles, SORT_THREADS, SORT_WARPS * nbins * 4, st>>>(
-        kin, vin, kout, vout, n, N, shift, nbins, hist, p.n_tiles);
+        kin, vin, kout, vout, n, N, shift, nbins, hist, tot);
     CTR_LAUNCHED("radix_scatter");
     kin = kout;
     vin = vout;
   }
   heads_count_kernel<<<p.n_tiles, SORT_THREADS, 0, st>>>(kin, n, tiles, p.n_tiles, long_list);
   CTR_LAUNCHED("heads_count");
-  scan_exclusive_kernel<<<1, 1024, 0, st>>>(tiles, p.n_tiles + 1);
-  CTR_LAUNCHED("heads_scan");
   heads_emit_kernel<<<p.n_tiles, SORT_THREADS, 0, st>>>(kin, perm, n, tiles, uniq, seg_offsets,
                                                         inverse, n_uniq);
   CTR_LAUNCHED("heads_emit");

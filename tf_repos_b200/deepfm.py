@@ -8,6 +8,9 @@ scatter-add, optimizer) runs in hand-written sm_100a kernels through the C ABI.
 update_mode
   "exact": TensorFlow semantics -- every table row moves every step (dense L2 gradient +
            non-lazy sparse Adam).  This is what `python DeepFM.py` computes.
+  "exact_deferred": bit-identical state to "exact", but the update of rows nothing gathered is
+           replayed lazily (csrc/epoch.cu): one pass over HBM per `epoch_steps` steps instead of one
+           per step.  The l2*l2_loss terms of `loss` become available at the end of each epoch.
   "lazy" : only gathered rows are updated (what LazyAdam would do); NOT the reference's result.
 """
 from __future__ import annotations
@@ -33,8 +36,8 @@ class DeepFM:
     def __init__(self, field_size: int, feature_size: int, embedding_size: int, batch_size: int,
                  deep_layers="256,128,64", dropout="0.5,0.5,0.5", l2_reg: float = 1e-4,
                  learning_rate: float = 5e-4, optimizer: str = "Adam", update_mode: str = "exact",
-                 device="cuda", seed: int = 0, world: int = 1):
-        assert update_mode in ("exact", "lazy")
+                 device="cuda", seed: int = 0, world: int = 1, epoch_steps: int = 8):
+        assert update_mode in ("exact", "exact_deferred", "lazy")
         self.F, self.N, self.K, self.B = field_size, feature_size, embedding_size, batch_size
         self.layers, self.keep = _ints(deep_layers), _floats(dropout)
         self.l2_reg, self.update_mode = float(l2_reg), update_mode
@@ -73,9 +76,22 @@ class DeepFM:
             self.g_rows_all = torch.empty(G * B * F, K, **f32)
             self.g_w_all = torch.empty(G * B * F, **f32)
         self.global_step = 0
+        self.epoch_steps, self.epoch_pos = epoch_steps, 0
+        if update_mode == "exact_deferred":
+            # Adagrad/Momentum/Ftrl with l2_reg == 0 are truly sparse in TF: nothing to defer
+            if self.l2_reg == 0.0 and optimizer != "Adam":
+                self.update_mode = "exact"
+            else:
+                self.updater.enable_epochs(epoch_steps, [self.fm_v, self.fm_w])
 
     # ---- variable access by TF name ------------------------------------------------------------------
+    def flush(self):
+        """exact_deferred: bring every row to the current step (no-op otherwise)."""
+        if self.update_mode == "exact_deferred" and self.epoch_pos > 0:
+            self.updater.epoch_sweep([self.fm_v, self.fm_w], self.epoch_pos, reset=False, l2_reg=self.l2_reg)
+
     def variables(self) -> Dict[str, torch.Tensor]:
+        self.flush()
         out = {"fm_v": self.fm_v.var, "fm_w": self.fm_w.var}
         out.update(self.dense.views)
         return out
@@ -96,6 +112,7 @@ class DeepFM:
     def predict(self, ids: torch.Tensor, vals: torch.Tensor) -> torch.Tensor:
         """mode == PREDICT (DeepFM.py:178-185): returns prob [B]."""
         B = ids.shape[0]
+        self.flush()
         _, y_d = self._forward(ids, vals, train=False)
         ops.logit_loss(self.dense["fm_bias"], self.y_w[:B], self.y_v[:B], y_d, None, B, y=self.y[:B],
                        pred=self.pred[:B])
@@ -115,26 +132,57 @@ class DeepFM:
         (the L2 terms are produced by the dense sweep in exact mode; zeros in lazy mode)."""
         B, F, K = ids.shape[0], self.F, self.K
         assert B == self.B, "train_step is specialised for the configured batch size"
-        self.opt.tick()
+        deferred = self.update_mode == "exact_deferred"
+        if deferred:
+            j = self.epoch_pos
+            if j == 0:
+                self.updater.epoch_begin()
+            self.opt.tick_epoch(j)
+            ids_u = ids.reshape(-1)
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.ids_all, ids_u)
+                ids_u = self.ids_all
+            # gathered rows (of every rank) must hold the state at the start of this step
+            self.updater.unique(ids_u)
+            self.updater.epoch_rows([(self.fm_v, None), (self.fm_w, None)], j, apply=False)
+        else:
+            self.opt.tick()
         a, y_d = self._forward(ids, vals, train=True, masks=masks)
         ops.logit_loss(self.dense["fm_bias"], self.y_w, self.y_v, y_d, labels, B, y=self.y, pred=self.pred,
                        loss_ce=self.loss_ce, dy=self.dy, dbias=self.dense.grads["fm_bias"], B_total=B * self.world)
         self.mlp.backward_out(a, self.dy, self.dense, self.d_last)
         dX = self.mlp.backward_hidden(self.x, self.d_last, self.dense)
         ops.fm_embed_bwd(vals, self.x, self.S, dX, self.dy, self.dy, K, ops.FM_DEEPFM, self.g_rows, self.g_w)
+        g_rows, g_w = self.g_rows, self.g_w
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_gather_into_tensor(self.ids_all, ids.reshape(-1))
+            if not deferred:
+                dist.all_gather_into_tensor(self.ids_all, ids.reshape(-1))
             dist.all_gather_into_tensor(self.g_rows_all, self.g_rows)
             dist.all_gather_into_tensor(self.g_w_all, self.g_w)
             dist.all_reduce(self.dense.grad)  # dense gradients + the loss tail, summed over ranks
-            self.updater.dedup(self.ids_all, self.g_rows_all, self.g_w_all)
+            g_rows, g_w = self.g_rows_all, self.g_w_all
+        if deferred:
+            self.updater.segment_sum(g_rows, g_w)
+            self.updater.epoch_rows([(self.fm_v, self.updater.g_uniq), (self.fm_w, self.updater.gw_uniq)],
+                                    self.epoch_pos, apply=True)
+            self.epoch_pos += 1
+            if self.epoch_pos == self.epoch_steps:
+                self.updater.epoch_sweep([self.fm_v, self.fm_w], self.epoch_steps, reset=True, l2_reg=self.l2_reg)
+                self.epoch_pos = 0
         else:
-            self.updater.dedup(ids.reshape(-1), self.g_rows, self.g_w)
-        self.updater.apply(self.fm_v, self.fm_w, exact=(self.update_mode == "exact"), l2_reg=self.l2_reg)
+            self.updater.dedup(self.ids_all if self.world > 1 else ids.reshape(-1), g_rows, g_w)
+            self.updater.apply(self.fm_v, self.fm_w, exact=(self.update_mode == "exact"), l2_reg=self.l2_reg)
         self.dense.apply()
         self.global_step += 1
         return torch.cat([self.loss_ce, self.updater.reg[1:2], self.updater.reg[0:1]])
+
+    def epoch_reg_terms(self) -> torch.Tensor:
+        """exact_deferred: [2, epoch_steps] = l2*l2_loss(fm_w), l2*l2_loss(fm_v) for every step of the
+        epoch that just ended (valid right after the step that closed the epoch)."""
+        ep = self.updater.ep
+        return torch.stack([ep["fm_w"]["reg"][: self.epoch_steps], ep["fm_v"]["reg"][: self.epoch_steps]])
 
     def loss_value(self, parts: torch.Tensor) -> float:
         p = parts.tolist()

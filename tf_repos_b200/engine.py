@@ -56,6 +56,14 @@ class OptimizerState:
         if self.name == "Adam":
             ops.adam_tick(self.state, self.hyper)
 
+    def tick_epoch(self, j: int):
+        """exact-deferred mode: like tick(), and records this step's lr_t in lr_table[j]."""
+        if self.lr_table is None:
+            self.lr_table = torch.zeros(ops.epoch_max_steps(), dtype=torch.float32, device=self.device)
+        ops.epoch_tick(self.state, self.hyper, self.lr_table, j, self.name == "Adam")
+
+    lr_table = None
+
     def record(self, which: int) -> torch.Tensor:
         return self.hyper[which]
 
@@ -111,6 +119,58 @@ class SparseUpdater:
     def dedup(self, ids_flat: torch.Tensor, g_rows: torch.Tensor, g_w: Optional[torch.Tensor]):
         ops.unique_segment(ids_flat, self.uw)
         ops.segment_sum_rows(g_rows, g_w, self.uw, self.K, self.g_uniq, self.gw_uniq if g_w is not None else None)
+
+    # ---- exact-deferred ("epoch") mode: csrc/epoch.cu ------------------------------------------------
+    def enable_epochs(self, P: int, tables: Sequence[Table]):
+        """Allocates the per-row `last` bytes and the per-step sum(var^2) accumulators."""
+        pmax = ops.epoch_max_steps()
+        assert 1 <= P <= pmax
+        dev = tables[0].var.device
+        self.P = P
+        self.n_epart = ops.epoch_partials_count()
+        self.ep = {}
+        for t in tables:
+            self.ep[t.name] = dict(
+                last=torch.zeros(t.N, dtype=torch.uint8, device=dev),
+                ss=torch.zeros(pmax, dtype=torch.float64, device=dev),
+                partials=torch.zeros(pmax * self.n_epart, dtype=torch.float64, device=dev),
+                reg=torch.zeros(pmax, dtype=torch.float32, device=dev))
+
+    def unique(self, ids_flat: torch.Tensor):
+        ops.unique_segment(ids_flat, self.uw)
+
+    def segment_sum(self, g_rows, g_w):
+        ops.segment_sum_rows(g_rows, g_w, self.uw, self.K, self.g_uniq, self.gw_uniq if g_w is not None else None)
+
+    def epoch_rows(self, tables_g, j: int, apply: bool):
+        """tables_g: [(Table, g_uniq or None)].  apply=False: catch the gathered rows up to the start of
+        step j; apply=True: take step j with the de-duplicated gradient."""
+        o, uw = self.opt, self.uw
+        for t, g in tables_g:
+            e = self.ep[t.name]
+            ops.epoch_rows(o.opt, apply, t.var, t.slot(0), t.slot(1), e["last"], uw.uniq, uw.n_uniq,
+                           g if apply else None, self.n, t.K, o.record(HYPER_TABLE), o.lr_table, j, e["ss"])
+
+    def epoch_sweep(self, tables: Sequence[Table], upto: int, reset: bool, l2_reg: float):
+        """All rows -> state after `upto` steps of this epoch; per-step l2*l2_loss terms -> ep[.]['reg']."""
+        o = self.opt
+        for t in tables:
+            e = self.ep[t.name]
+            ev = None
+            if self.sweep_events is not None and t.K > 1:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            ops.epoch_sweep(o.opt, t.var, t.slot(0), t.slot(1), e["last"], t.N, t.K, o.record(HYPER_TABLE),
+                            o.lr_table, upto, reset, e["partials"])
+            if ev is not None:
+                ev[1].record()
+                self.sweep_events.append(ev)
+            # accumulate: a mid-epoch flush and the epoch-end sweep each contribute their share
+            ops.epoch_reg_loss(e["ss"], e["partials"], self.n_epart, upto, 0.5 * l2_reg, e["reg"], accumulate=True)
+
+    def epoch_begin(self):
+        for e in self.ep.values():
+            ops.fill(e["reg"], 0.0)
 
     def apply(self, V: Table, W: Optional[Table], exact: bool, l2_reg: float):
         o, uw, hyper = self.opt, self.uw, self.opt.record(HYPER_TABLE)

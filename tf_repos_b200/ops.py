@@ -157,6 +157,51 @@ def adam_tick(state, hyper):
                            hyper.numel() // 8, _stream()), "ctr_adam_tick")
 
 
+def epoch_max_steps() -> int:
+    return int(_L.ctr_epoch_max_steps())
+
+
+def epoch_tick(state, hyper, lr_table, j: int, is_adam: bool):
+    check(_L.ctr_epoch_tick(_p(state, torch.float32, "state"), _p(hyper, torch.float32, "hyper"),
+                            hyper.numel() // 8, _p(lr_table, torch.float32, "lr_table"), j, int(is_adam),
+                            _stream()), "ctr_epoch_tick")
+
+
+def epoch_rows(opt, apply: bool, var, slot0, slot1, last, uniq, n_uniq, g_uniq, n_max, K, hyper, lr_table, j, ss):
+    check(
+        _L.ctr_epoch_rows(
+            opt, int(apply), _p(var, torch.float32, "var"), _p(slot0, torch.float32, "slot0"),
+            _p(slot1, torch.float32, "slot1"), _p(last, torch.uint8, "last"), _p(uniq, torch.int32, "uniq"),
+            _p(n_uniq, torch.int32, "n_uniq"), _p(g_uniq, torch.float32, "g_uniq"), n_max, K,
+            _p(hyper, torch.float32, "hyper"), _p(lr_table, torch.float32, "lr_table"), j,
+            _p(ss, torch.float64, "ss"), _stream()),
+        "ctr_epoch_rows")
+
+
+def epoch_partials_count() -> int:
+    return int(_L.ctr_device_sm_count()) * 3
+
+
+def epoch_sweep(opt, var, slot0, slot1, last, n_rows, K, hyper, lr_table, upto: int, reset: bool, ss_partials):
+    n_part = ctypes.c_int(0)
+    check(
+        _L.ctr_epoch_sweep(
+            opt, _p(var, torch.float32, "var"), _p(slot0, torch.float32, "slot0"),
+            _p(slot1, torch.float32, "slot1"), _p(last, torch.uint8, "last"), n_rows, K,
+            _p(hyper, torch.float32, "hyper"), _p(lr_table, torch.float32, "lr_table"), upto, int(reset),
+            _p(ss_partials, torch.float64, "ss_partials"), ctypes.byref(n_part), _stream()),
+        "ctr_epoch_sweep")
+    return n_part.value
+
+
+def epoch_reg_loss(ss_rows, ss_partials, n_partials, upto, scale, reg, accumulate=False):
+    check(
+        _L.ctr_epoch_reg_loss(_p(ss_rows, torch.float64, "ss_rows"), _p(ss_partials, torch.float64, "ss_partials"),
+                              n_partials, upto, float(scale), _p(reg, torch.float32, "reg"), int(accumulate),
+                              _stream()),
+        "ctr_epoch_reg_loss")
+
+
 def reduce_sum(inp, scale, out, ws):
     check(
         _L.ctr_reduce_sum(_p(inp, torch.float32, "in"), inp.numel(), float(scale), _p(out, torch.float32, "out"),
