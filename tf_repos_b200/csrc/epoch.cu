@@ -164,7 +164,9 @@ epoch_sweep_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __
   const int sh = 31 - __clz(f4_per_row);
   auto row_of = [&](int64_t i) { return pow2 ? (i >> sh) : (i / f4_per_row); };
   auto row_head = [&](int64_t i) { return pow2 ? ((i & (f4_per_row - 1)) == 0) : ((i % f4_per_row) == 0); };
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += UNROLL * stride) {
+  // the loop bound is WARP-UNIFORM (the body contains full-mask shuffles); lanes past n4 are masked
+  for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < n4; w0 += UNROLL * stride) {
+    const int64_t i0 = w0 + (threadIdx.x & 31);
     float4 x[UNROLL], a[UNROLL], b[UNROLL];
     int l0[UNROLL];
 #pragma unroll
