@@ -90,6 +90,16 @@ class DeepFM:
         if self.update_mode == "exact_deferred" and self.epoch_pos > 0:
             self.updater.epoch_sweep([self.fm_v, self.fm_w], self.epoch_pos, reset=False, l2_reg=self.l2_reg)
 
+    def set_update_mode(self, mode: str):
+        """Switch between exact / exact_deferred / lazy on a live model (state stays consistent)."""
+        assert mode in ("exact", "exact_deferred", "lazy")
+        if self.update_mode == "exact_deferred" and self.epoch_pos > 0:
+            self.updater.epoch_sweep([self.fm_v, self.fm_w], self.epoch_pos, reset=True, l2_reg=self.l2_reg)
+            self.epoch_pos = 0
+        if mode == "exact_deferred" and not hasattr(self.updater, "ep"):
+            self.updater.enable_epochs(self.epoch_steps, [self.fm_v, self.fm_w])
+        self.update_mode = mode
+
     def variables(self) -> Dict[str, torch.Tensor]:
         self.flush()
         out = {"fm_v": self.fm_v.var, "fm_w": self.fm_w.var}
