@@ -192,6 +192,32 @@ int ctr_logit_loss(const float* bias, const float* y_a, const float* y_b, const 
                    const float* labels, int B, int B_total, float* y, float* pred, float* loss_ce,
                    float* dy, float* dbias, ctr_stream_t stream);
 
+/* ---- dense layers: fp32 SIMT GEMMs with fused epilogues -------------------------------------------
+ * tf.contrib.layers.fully_connected (DeepFM.py:156,165) + tf.nn.dropout (:162) and their autodiff.
+ *   fwd: out[M,Nd] = dropout(act(in[M,Kd] @ Wt[Kd,Nd] + b)),  act 0 = identity, 1 = relu;
+ *        drop_mask = binary keep mask [M,Nd] (NULL = no dropout): out = x / keep_prob * mask.
+ *   bwd: dOut is overwritten with dZ = (dOut*mask/keep) * (out > 0);  db = colsum(dZ);
+ *        dW = in^T @ dZ (split over M, deterministic);  dIn = dZ @ Wt^T (NULL to skip).
+ * fc1: the N = 1 output layer over the concatenation [in_a | in_b] (in_b NULL/Kb = 0 for DeepFM's
+ *      deep_out; DCN's out_layer takes [x_L, x_deep], DCN.py:178-181).
+ * Accumulation order is fixed => bit-reproducible. */
+int ctr_fc_fwd(const float* in, const float* Wt, const float* b, const float* drop_mask, float keep_prob,
+               int M, int Kd, int Nd, int act, float* out, ctr_stream_t stream);
+size_t ctr_fc_bwd_workspace_bytes(int M, int Kd, int Nd);
+int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* drop_mask, float keep_prob,
+               float* dOut, int M, int Kd, int Nd, int act, float* dIn, float* dW, float* db, void* ws,
+               size_t ws_bytes, ctr_stream_t stream);
+int ctr_fc1_fwd(const float* in_a, int Ka, const float* in_b, int Kb, const float* w, const float* b, int M,
+                float* y, ctr_stream_t stream);
+size_t ctr_fc1_bwd_workspace_bytes(int M, int Ka, int Kb);
+int ctr_fc1_bwd(const float* in_a, int Ka, const float* in_b, int Kb, const float* w, const float* dy, int M,
+                float* d_a, float* d_b, float* dw, float* db, void* ws, size_t ws_bytes, ctr_stream_t stream);
+/* binary keep mask: mask[i] = (hash(seed, *step_dev, i) < keep_prob) -- tf.nn.dropout's
+ * floor(keep_prob + uniform); step_dev = device float holding the global step (NULL = 0) so that a
+ * captured graph draws a fresh mask every replay.  Not TF's Philox stream. */
+int ctr_dropout_mask(float* mask, int64_t n, float keep_prob, uint64_t seed, const float* step_dev,
+                     ctr_stream_t stream);
+
 /* ---- table initialisation (glorot_normal_initializer, DeepFM.py:115-116; truncated at 2 sigma) --- */
 int ctr_init_trunc_normal(float* t, int64_t n, float stddev, uint64_t seed, ctr_stream_t stream);
 int ctr_fill(float* t, int64_t n, float value, ctr_stream_t stream);

@@ -367,3 +367,77 @@ def test_init_trunc_normal_distribution():
     assert abs(t.std().item() / 0.01 - 0.8796) < 0.01
     t2 = torch.empty_like(t); ops.init_trunc_normal(t2, 0.01, 123)
     assert torch.equal(t, t2)
+
+
+# -------------------------------------------------------------------------------------------------
+# dense layers (csrc/fc.cu) vs fp64 torch
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,Kd,Nd", [(8192, 624, 256), (8192, 256, 128), (1000, 128, 64), (37, 50, 19), (256, 312, 400)])
+@pytest.mark.parametrize("drop", [False, True])
+def test_fc_fwd_bwd(M, Kd, Nd, drop):
+    from tf_repos_b200 import ops
+    d = _dev()
+    g = torch.Generator().manual_seed(M + Nd)
+    x = torch.randn(M, Kd, generator=g); W = torch.randn(Kd, Nd, generator=g) / Kd ** 0.5
+    b = torch.randn(Nd, generator=g) * 0.1
+    keep = 0.8
+    mask = (torch.rand(M, Nd, generator=g) < keep).float() if drop else None
+    dOut = torch.randn(M, Nd, generator=g)
+    xd, Wd, bd = x.double().requires_grad_(), W.double().requires_grad_(), b.double().requires_grad_()
+    z = torch.relu(xd @ Wd + bd)
+    out_ref = z / keep * mask.double() if drop else z
+    out_ref.backward(dOut.double())
+    out = torch.empty(M, Nd, device=d)
+    ops.fc_fwd(x.to(d), W.to(d), b.to(d), mask.to(d) if drop else None, keep, 1, out)
+    _close(out, out_ref, rtol=2e-6 * Kd ** 0.5, what="fc out")
+    dO = dOut.to(d).clone()
+    dIn = torch.empty(M, Kd, device=d); dW = torch.empty(Kd, Nd, device=d); db = torch.empty(Nd, device=d)
+    ws = torch.empty(ops.fc_bwd_workspace_bytes(M, Kd, Nd), dtype=torch.uint8, device=d)
+    ops.fc_bwd(x.to(d), W.to(d), out, mask.to(d) if drop else None, keep, dO, 1, dIn, dW, db, ws)
+    _close(dIn, xd.grad, rtol=1e-5, what="dIn")
+    _close(dW, Wd.grad, rtol=1e-5, what="dW")
+    _close(db, bd.grad, rtol=1e-5, what="db")
+    # determinism
+    dW2 = torch.empty_like(dW); dO2 = dOut.to(d).clone()
+    ops.fc_bwd(x.to(d), W.to(d), out, mask.to(d) if drop else None, keep, dO2, 1, None, dW2, db, ws)
+    assert torch.equal(dW, dW2)
+
+
+@pytest.mark.parametrize("Ka,Kb", [(64, 0), (624, 64), (5, 3)])
+def test_fc1_fwd_bwd(Ka, Kb):
+    from tf_repos_b200 import ops
+    d = _dev()
+    M = 777
+    g = torch.Generator().manual_seed(Ka)
+    a = torch.randn(M, Ka, generator=g); bb = torch.randn(M, Kb, generator=g) if Kb else None
+    w = torch.randn(Ka + Kb, generator=g); bias = torch.tensor([0.3]); dy = torch.randn(M, generator=g)
+    cat = torch.cat([a, bb], 1) if Kb else a
+    catd, wd, bd = cat.double().requires_grad_(), w.double().requires_grad_(), bias.double().requires_grad_()
+    y_ref = catd @ wd + bd
+    y_ref.backward(dy.double())
+    y = torch.empty(M, device=d)
+    ops.fc1_fwd(a.to(d), bb.to(d) if Kb else None, w.to(d), bias.to(d), y)
+    _close(y, y_ref, rtol=1e-5)
+    d_a = torch.empty(M, Ka, device=d); d_b = torch.empty(M, Kb, device=d) if Kb else None
+    dw = torch.empty(Ka + Kb, device=d); db = torch.empty(1, device=d)
+    ws = torch.empty(ops.fc1_bwd_workspace_bytes(M, Ka, Kb), dtype=torch.uint8, device=d)
+    ops.fc1_bwd(a.to(d), bb.to(d) if Kb else None, w.to(d), dy.to(d), d_a, d_b, dw, db, ws)
+    _close(d_a, catd.grad[:, :Ka], rtol=1e-6)
+    if Kb:
+        _close(d_b, catd.grad[:, Ka:], rtol=1e-6)
+    _close(dw, wd.grad, rtol=1e-5)
+    _close(db, bd.grad, scale=dy.abs().sum(), rtol=1e-5)
+
+
+def test_dropout_mask_rate_and_step_dependence():
+    from tf_repos_b200 import ops
+    d = _dev()
+    m = torch.empty(1_000_000, device=d); m2 = torch.empty_like(m)
+    step = torch.tensor([3.0], device=d)
+    ops.dropout_mask(m, 0.8, 7, step)
+    assert set(m.unique().tolist()) <= {0.0, 1.0} and abs(m.mean().item() - 0.8) < 2e-3
+    ops.dropout_mask(m2, 0.8, 7, step)
+    assert torch.equal(m, m2)
+    step.fill_(4.0)
+    ops.dropout_mask(m2, 0.8, 7, step)
+    assert not torch.equal(m, m2)

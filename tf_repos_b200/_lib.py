@@ -56,6 +56,13 @@ SIGNATURES = {
     "ctr_l2_loss_workspace_bytes": (c_size_t, [c_int64]),
     "ctr_l2_loss": (c_int, [P, c_int64, P, P, c_size_t, P]),
     "ctr_logit_loss": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P]),
+    "ctr_fc_fwd": (c_int, [P, P, P, P, c_float, c_int, c_int, c_int, c_int, P, P]),
+    "ctr_fc_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ctr_fc_bwd": (c_int, [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "ctr_fc1_fwd": (c_int, [P, c_int, P, c_int, P, P, c_int, P, P]),
+    "ctr_fc1_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ctr_fc1_bwd": (c_int, [P, c_int, P, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
+    "ctr_dropout_mask": (c_int, [P, c_int64, c_float, c_uint64, P, P]),
     "ctr_init_trunc_normal": (c_int, [P, c_int64, c_float, c_uint64, P]),
     "ctr_fill": (c_int, [P, c_int64, c_float, P]),
 }

@@ -115,7 +115,7 @@ class DeepFM:
         B = ids.shape[0]
         ops.fm_embed_fwd(ids, vals, self.fm_v.var, self.fm_w.var, ops.FM_DEEPFM, x=self.x[:B], y_w=self.y_w[:B],
                          y2=self.y_v[:B], S=self.S[:B], oob=self.oob)
-        a = self.mlp.forward_hidden(self.x[:B], self.dense, train, masks)
+        a = self.mlp.forward_hidden(self.x[:B], self.dense, train, masks, step_dev=self.opt.state[3:4])
         y_d = self.mlp.forward_out(a, self.dense)
         return a, y_d
 

@@ -55,6 +55,8 @@ class OptimizerState:
         """Start of a step.  For Adam: lr_t from the current beta powers, then advance them."""
         if self.name == "Adam":
             ops.adam_tick(self.state, self.hyper)
+        else:  # only the global-step counter advances (it seeds the dropout masks)
+            self.tick_epoch(0)
 
     def tick_epoch(self, j: int):
         """exact-deferred mode: like tick(), and records this step's lr_t in lr_table[j]."""

@@ -1,12 +1,13 @@
-"""The dense 'Deep-part' (DeepFM.py:137-167): fully_connected(relu) -> [BN] -> dropout stacks.
+"""The dense 'Deep-part' (DeepFM.py:137-167): fully_connected(relu) -> dropout stacks + the N=1 output
+layer, forward and backward, through libctr_b200.so (csrc/fc.cu).  No torch compute.
 
-fp32 throughout (logit parity target is 1e-5 relative, which rules out TF32/BF16 tensor-core
-inputs without split-precision emulation).  Forward/backward buffers are allocated once so the
-whole step can be captured in a CUDA graph.
+fp32 throughout (the logit parity target is 1e-5 relative, which rules out TF32/BF16 tensor-core
+inputs without split-precision emulation).  All buffers are allocated once (CUDA-graph capturable).
+batch_norm=True (tf.contrib.layers.batch_norm, DeepFM.py:231-235) is not on this path yet.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 
@@ -15,19 +16,29 @@ from .engine import DenseVars
 
 
 class MLP:
-    """layers: hidden widths; final_out: append a Linear(->1, identity) named `{scope}/{out_scope}`."""
+    """layers: hidden widths; the output layer `{scope}/{out_scope}` maps [last hidden | extra] -> 1."""
 
     def __init__(self, in_dim: int, layers: Sequence[int], keep_prob: Sequence[float], B: int, device,
-                 scope: str = "Deep-part", out_scope: Optional[str] = "deep_out", out_extra_in: int = 0):
+                 scope: str = "Deep-part", out_scope: Optional[str] = "deep_out", out_extra_in: int = 0,
+                 seed: int = 0):
         self.in_dim, self.layers, self.keep = in_dim, list(layers), list(keep_prob)
         self.scope, self.out_scope, self.B, self.device = scope, out_scope, B, device
-        self.out_in = (self.layers[-1] if self.layers else in_dim) + out_extra_in
+        self.last_dim = self.layers[-1] if self.layers else in_dim
+        self.out_extra_in = out_extra_in
+        self.out_in = self.last_dim + out_extra_in
+        self.seed = seed
         f32 = dict(dtype=torch.float32, device=device)
-        self.h = [torch.empty(B, w, **f32) for w in self.layers]          # post-activation (post-dropout)
-        self.mask = [None] * len(self.layers)                              # keep-scaled dropout masks
+        self.h = [torch.empty(B, w, **f32) for w in self.layers]          # post-activation, post-dropout
+        self.masks = [torch.empty(B, w, **f32) if k < 1.0 else None for w, k in zip(self.layers, self.keep)]
         self.dh = [torch.empty(B, w, **f32) for w in self.layers]
         self.y = torch.empty(B, **f32)
         self.dx = torch.empty(B, in_dim, **f32)
+        self.d_extra = torch.empty(B, out_extra_in, **f32) if out_extra_in else None
+        dims = [in_dim] + self.layers
+        ws = max([ops.fc_bwd_workspace_bytes(B, dims[i], dims[i + 1]) for i in range(len(self.layers))] +
+                 [ops.fc1_bwd_workspace_bytes(B, self.last_dim, out_extra_in), 16])
+        self.ws = torch.empty(ws, dtype=torch.uint8, device=device)
+        self._active = [None] * len(self.layers)
 
     def specs(self):
         out, d = [], self.in_dim
@@ -48,54 +59,57 @@ class MLP:
                 dv[name].copy_(w.to(torch.float32))
 
     # ---- forward -------------------------------------------------------------------------------
-    def forward_hidden(self, x: torch.Tensor, dv: DenseVars, train: bool, masks=None) -> torch.Tensor:
+    def forward_hidden(self, x: torch.Tensor, dv: DenseVars, train: bool, masks=None, step_dev=None) -> torch.Tensor:
+        """masks: optional injected binary keep masks (parity runs); otherwise, in TRAIN mode with
+        keep_prob < 1, a fresh mask is drawn on the device from (seed, global step, element)."""
         a = x
+        n = a.shape[0]
         for i in range(len(self.layers)):
             W, b = dv[f"{self.scope}/mlp{i}/weights"], dv[f"{self.scope}/mlp{i}/biases"]
-            h = self.h[i][: a.shape[0]]
-            torch.addmm(b, a, W, out=h)
-            h.relu_()
-            self.mask[i] = None
-            if train and (masks is not None or self.keep[i] < 1.0):
-                if masks is not None:
-                    m = masks[i] / self.keep[i]
-                else:
-                    m = torch.empty_like(h).bernoulli_(self.keep[i]).div_(self.keep[i])
-                self.mask[i] = m
-                h.mul_(m)
+            m = None
+            if train and masks is not None and masks[i] is not None:
+                m = masks[i]
+            elif train and self.keep[i] < 1.0:
+                m = self.masks[i][:n]
+                ops.dropout_mask(m, self.keep[i], self.seed * 131 + i, step_dev)
+            self._active[i] = m
+            h = self.h[i][:n]
+            ops.fc_fwd(a, W, b, m, self.keep[i], 1, h)
             a = h
         return a
 
-    def forward_out(self, a: torch.Tensor, dv: DenseVars) -> torch.Tensor:
+    def forward_out(self, a: torch.Tensor, dv: DenseVars, extra: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """y = [extra | a] @ W + b when `extra` is given (DCN: [x_L, x_deep]), else a @ W + b."""
         W, b = dv[f"{self.scope}/{self.out_scope}/weights"], dv[f"{self.scope}/{self.out_scope}/biases"]
         y = self.y[: a.shape[0]]
-        torch.addmv(b.expand(a.shape[0]), a, W.view(-1), out=y)
+        if extra is not None:
+            ops.fc1_fwd(extra, a, W.view(-1), b, y)
+        else:
+            ops.fc1_fwd(a, None, W.view(-1), b, y)
         return y
 
     # ---- backward ------------------------------------------------------------------------------
-    def backward_out(self, a: torch.Tensor, dy: torch.Tensor, dv: DenseVars, da: torch.Tensor):
-        """y = a @ W + b ; dy [B] -> dW, db, da."""
+    def backward_out(self, a: torch.Tensor, dy: torch.Tensor, dv: DenseVars, da: torch.Tensor,
+                     extra: Optional[torch.Tensor] = None):
         W = dv[f"{self.scope}/{self.out_scope}/weights"]
-        torch.mv(a.t(), dy, out=dv.grads[f"{self.scope}/{self.out_scope}/weights"].view(-1))
-        torch.sum(dy, dim=0, keepdim=True, out=dv.grads[f"{self.scope}/{self.out_scope}/biases"])
-        torch.mul(dy.unsqueeze(1), W.view(1, -1), out=da)
+        gW = dv.grads[f"{self.scope}/{self.out_scope}/weights"].view(-1)
+        gb = dv.grads[f"{self.scope}/{self.out_scope}/biases"]
+        if extra is not None:
+            ops.fc1_bwd(extra, a, W.view(-1), dy, self.d_extra[: a.shape[0]], da, gW, gb, self.ws)
+        else:
+            ops.fc1_bwd(a, None, W.view(-1), dy, da, None, gW, gb, self.ws)
 
     def backward_hidden(self, x: torch.Tensor, d_last: torch.Tensor, dv: DenseVars, need_dx: bool = True):
-        """d_last: gradient w.r.t. the last hidden activation (post-dropout)."""
+        """d_last: gradient w.r.t. the last hidden activation (post-dropout); overwritten."""
         d = d_last
+        n = d.shape[0]
+        if not self.layers:
+            return d_last
         for i in reversed(range(len(self.layers))):
             W = dv[f"{self.scope}/mlp{i}/weights"]
-            h = self.h[i][: d.shape[0]]
-            if self.mask[i] is not None:
-                d.mul_(self.mask[i])
-            d.mul_(h > 0)  # relu' (h is post-dropout: h>0 iff relu output >0 and kept)
-            a = self.h[i - 1][: d.shape[0]] if i > 0 else x
-            torch.mm(a.t(), d, out=dv.grads[f"{self.scope}/mlp{i}/weights"])
-            torch.sum(d, dim=0, out=dv.grads[f"{self.scope}/mlp{i}/biases"])
-            if i > 0:
-                nd = self.dh[i - 1][: d.shape[0]]
-                torch.mm(d, W.t(), out=nd)
-                d = nd
-            elif need_dx:
-                torch.mm(d, W.t(), out=self.dx[: d.shape[0]])
-        return self.dx[: d.shape[0]] if need_dx else None
+            a = self.h[i - 1][:n] if i > 0 else x
+            d_in = self.dh[i - 1][:n] if i > 0 else (self.dx[:n] if need_dx else None)
+            ops.fc_bwd(a, W, self.h[i][:n], self._active[i], self.keep[i], d, 1, d_in,
+                       dv.grads[f"{self.scope}/mlp{i}/weights"], dv.grads[f"{self.scope}/mlp{i}/biases"], self.ws)
+            d = d_in
+        return self.dx[:n] if need_dx else None

@@ -157,6 +157,53 @@ def adam_tick(state, hyper):
                            hyper.numel() // 8, _stream()), "ctr_adam_tick")
 
 
+def fc_fwd(inp, Wt, b, drop_mask, keep_prob, act, out):
+    M, Kd = inp.shape
+    Nd = Wt.shape[1]
+    check(_L.ctr_fc_fwd(_p(inp, torch.float32, "in"), _p(Wt, torch.float32, "Wt"), _p(b, torch.float32, "b"),
+                        _p(drop_mask, torch.float32, "drop_mask"), float(keep_prob), M, Kd, Nd, act,
+                        _p(out, torch.float32, "out"), _stream()), "ctr_fc_fwd")
+
+
+def fc_bwd_workspace_bytes(M, Kd, Nd) -> int:
+    return int(_L.ctr_fc_bwd_workspace_bytes(M, Kd, Nd))
+
+
+def fc_bwd(inp, Wt, out, drop_mask, keep_prob, dOut, act, dIn, dW, db, ws):
+    M, Kd = inp.shape
+    Nd = Wt.shape[1]
+    check(_L.ctr_fc_bwd(_p(inp, torch.float32, "in"), _p(Wt, torch.float32, "Wt"), _p(out, torch.float32, "out"),
+                        _p(drop_mask, torch.float32, "drop_mask"), float(keep_prob), _p(dOut, torch.float32, "dOut"),
+                        M, Kd, Nd, act, _p(dIn, torch.float32, "dIn"), _p(dW, torch.float32, "dW"),
+                        _p(db, torch.float32, "db"), _p(ws), ws.numel() * ws.element_size(), _stream()), "ctr_fc_bwd")
+
+
+def fc1_fwd(in_a, in_b, w, b, y):
+    M, Ka = in_a.shape
+    Kb = in_b.shape[1] if in_b is not None else 0
+    check(_L.ctr_fc1_fwd(_p(in_a, torch.float32, "in_a"), Ka, _p(in_b, torch.float32, "in_b"), Kb,
+                         _p(w, torch.float32, "w"), _p(b, torch.float32, "b"), M, _p(y, torch.float32, "y"),
+                         _stream()), "ctr_fc1_fwd")
+
+
+def fc1_bwd_workspace_bytes(M, Ka, Kb) -> int:
+    return int(_L.ctr_fc1_bwd_workspace_bytes(M, Ka, Kb))
+
+
+def fc1_bwd(in_a, in_b, w, dy, d_a, d_b, dw, db, ws):
+    M, Ka = in_a.shape
+    Kb = in_b.shape[1] if in_b is not None else 0
+    check(_L.ctr_fc1_bwd(_p(in_a, torch.float32, "in_a"), Ka, _p(in_b, torch.float32, "in_b"), Kb,
+                         _p(w, torch.float32, "w"), _p(dy, torch.float32, "dy"), M, _p(d_a, torch.float32, "d_a"),
+                         _p(d_b, torch.float32, "d_b"), _p(dw, torch.float32, "dw"), _p(db, torch.float32, "db"),
+                         _p(ws), ws.numel() * ws.element_size(), _stream()), "ctr_fc1_bwd")
+
+
+def dropout_mask(mask, keep_prob, seed, step_dev=None):
+    check(_L.ctr_dropout_mask(_p(mask, torch.float32, "mask"), mask.numel(), float(keep_prob), int(seed),
+                              _p(step_dev, torch.float32, "step"), _stream()), "ctr_dropout_mask")
+
+
 def epoch_max_steps() -> int:
     return int(_L.ctr_epoch_max_steps())
 
