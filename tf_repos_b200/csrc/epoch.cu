@@ -15,6 +15,8 @@
 //
 // Replaces the same reference lines as optim.cu: optimizer.minimize (DeepFM.py:204-213) with the
 // dense l2_loss gradient (DeepFM.py:189-190) [TF-sem].
+#include <stdlib.h>
+
 #include "optim_steps.cuh"
 
 namespace ctr {
@@ -37,8 +39,8 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
                   double* __restrict__ ss) {
   constexpr int K = 4 * LPR * VEC;
   constexpr bool two = OptTraits<OPT>::slots == 2;
-  __shared__ double ss_blk[EPOCH_MAX];
-  if (threadIdx.x < EPOCH_MAX) ss_blk[threadIdx.x] = 0.0;
+  __shared__ float ss_blk[EPOCH_MAX];  // <= 256 rows' worth per CTA: fp32 is plenty; global sums are double
+  if (threadIdx.x < EPOCH_MAX) ss_blk[threadIdx.x] = 0.f;
   __syncthreads();
   const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int c = threadIdx.x % LPR;
@@ -63,7 +65,7 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
       float q = 0.f;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) { q += sq4(x[v]); step_untouched4<OPT>(x[v], a[v], b[v], h); }
-      atomicAdd(&ss_blk[s], (double)q);
+      atomicAdd(&ss_blk[s], q);
     }
     if (APPLY) {
       h.lr = lr_table[j];
@@ -76,7 +78,7 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
                         __fadd_rn(g.z, __fmul_rn(h.l2, x[v].z)), __fadd_rn(g.w, __fmul_rn(h.l2, x[v].w)));
         step_sparse4<OPT>(x[v], a[v], b[v], g, h);
       }
-      atomicAdd(&ss_blk[j], (double)q);
+      atomicAdd(&ss_blk[j], q);
     }
     if (APPLY || l0 < j) {
 #pragma unroll
@@ -91,7 +93,7 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
   }
   __syncthreads();  // every lane of a row has read `last` before lane 0 of the row rewrites it
   if (wrote && c == 0) last[id] = (uint8_t)(APPLY ? j + 1 : j);
-  if (threadIdx.x < EPOCH_MAX && ss_blk[threadIdx.x] != 0.0) atomicAdd(&ss[threadIdx.x], ss_blk[threadIdx.x]);
+  if (threadIdx.x < EPOCH_MAX && ss_blk[threadIdx.x] != 0.f) atomicAdd(&ss[threadIdx.x], (double)ss_blk[threadIdx.x]);
 }
 
 // any K (incl. the scalar first-order table, K = 1): one thread per (row, k)
@@ -103,8 +105,8 @@ epoch_rows_generic_kernel(float* __restrict__ var, float* __restrict__ slot0, fl
                           int64_t n_max, int K, const float* __restrict__ hyper,
                           const float* __restrict__ lr_table, int j, double* __restrict__ ss) {
   constexpr bool two = OptTraits<OPT>::slots == 2;
-  __shared__ double ss_blk[EPOCH_MAX];
-  if (threadIdx.x < EPOCH_MAX) ss_blk[threadIdx.x] = 0.0;
+  __shared__ float ss_blk[EPOCH_MAX];
+  if (threadIdx.x < EPOCH_MAX) ss_blk[threadIdx.x] = 0.f;
   __syncthreads();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t u = t / K;
@@ -117,12 +119,12 @@ epoch_rows_generic_kernel(float* __restrict__ var, float* __restrict__ slot0, fl
     float x = var[e], a = slot0[e], b = two ? slot1[e] : 0.f;
     for (int s = l0; s < j; ++s) {
       h.lr = lr_table[s];
-      atomicAdd(&ss_blk[s], (double)(x * x));
+      atomicAdd(&ss_blk[s], x * x);
       step_sparse<OPT>(x, a, b, __fmul_rn(h.l2, x), h);
     }
     if (APPLY) {
       h.lr = lr_table[j];
-      atomicAdd(&ss_blk[j], (double)(x * x));
+      atomicAdd(&ss_blk[j], x * x);
       step_sparse<OPT>(x, a, b, __fadd_rn(g_uniq[u * K + k], __fmul_rn(h.l2, x)), h);
     }
     if (APPLY || l0 < j) {
@@ -134,7 +136,7 @@ epoch_rows_generic_kernel(float* __restrict__ var, float* __restrict__ slot0, fl
   // admits K that divide 256 here, so a row never straddles two CTAs
   __syncthreads();
   if (u < n_max && u < n_uniq[0] && k == 0) last[uniq[u]] = (uint8_t)(APPLY ? j + 1 : j);
-  if (threadIdx.x < EPOCH_MAX && ss_blk[threadIdx.x] != 0.0) atomicAdd(&ss[threadIdx.x], ss_blk[threadIdx.x]);
+  if (threadIdx.x < EPOCH_MAX && ss_blk[threadIdx.x] != 0.f) atomicAdd(&ss[threadIdx.x], (double)ss_blk[threadIdx.x]);
 }
 
 // All rows: replay steps last[row]..upto-1, reset `last` where it was non-zero (reset == true) or
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(256, MINB)
 epoch_sweep_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
                    uint8_t* __restrict__ last, int64_t n4, int K, const float* __restrict__ hyper,
                    const float* __restrict__ lr_table, int upto, int reset,
-                   double* __restrict__ ss_partials) {
+                   double* __restrict__ ss_partials, int n_partials) {
   constexpr bool two = OptTraits<OPT>::slots == 2;
   __shared__ float lr_s[EPOCH_MAX];
   __shared__ double ss_blk[EPOCH_MAX];
@@ -211,7 +213,67 @@ epoch_sweep_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __
     }
   }
   __syncthreads();
-  if (threadIdx.x < upto) ss_partials[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = ss_blk[threadIdx.x];
+  if (threadIdx.x < upto) ss_partials[(int64_t)threadIdx.x * n_partials + blockIdx.x] = ss_blk[threadIdx.x];
+}
+
+// K == 1 (first-order weights fm_w): a float4 spans 4 rows, each with its own `last` byte
+template <int OPT>
+__global__ void __launch_bounds__(256)
+epoch_sweep_k1_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
+                      uint8_t* __restrict__ last, int64_t n4, const float* __restrict__ hyper,
+                      const float* __restrict__ lr_table, int upto, int reset,
+                      double* __restrict__ ss_partials, int n_partials) {
+  constexpr bool two = OptTraits<OPT>::slots == 2;
+  __shared__ float lr_s[EPOCH_MAX];
+  __shared__ double ss_blk[EPOCH_MAX];
+  if (threadIdx.x < EPOCH_MAX) {
+    lr_s[threadIdx.x] = (threadIdx.x < upto) ? lr_table[threadIdx.x] : 0.f;
+    ss_blk[threadIdx.x] = 0.0;
+  }
+  __syncthreads();
+  Hyper h = load_hyper(hyper);
+  float4* v4 = reinterpret_cast<float4*>(var);
+  float4* a4 = reinterpret_cast<float4*>(slot0);
+  float4* b4 = reinterpret_cast<float4*>(slot1);
+  uint32_t* l4 = reinterpret_cast<uint32_t*>(last);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < n4; w0 += stride) {
+    const int64_t i = w0 + (threadIdx.x & 31);
+    const bool ok = i < n4;
+    float4 x = f4_zero(), a = f4_zero(), b = f4_zero();
+    uint32_t lw = 0;
+    if (ok) {
+      x = ld_stream4(v4 + i); a = ld_stream4(a4 + i); b = two ? ld_stream4(b4 + i) : f4_zero();
+      lw = l4[i];
+    }
+    const int l0 = ok ? (int)(lw & 255u) : upto, l1 = ok ? (int)((lw >> 8) & 255u) : upto;
+    const int l2_ = ok ? (int)((lw >> 16) & 255u) : upto, l3 = ok ? (int)(lw >> 24) : upto;
+#pragma unroll 1
+    for (int s = 0; s < upto; ++s) {
+      h.lr = lr_s[s];
+      float q = 0.f;
+      if (s >= l0) { q += x.x * x.x; step_sparse<OPT>(x.x, a.x, b.x, __fmul_rn(h.l2, x.x), h); }
+      if (s >= l1) { q += x.y * x.y; step_sparse<OPT>(x.y, a.y, b.y, __fmul_rn(h.l2, x.y), h); }
+      if (s >= l2_) { q += x.z * x.z; step_sparse<OPT>(x.z, a.z, b.z, __fmul_rn(h.l2, x.z), h); }
+      if (s >= l3) { q += x.w * x.w; step_sparse<OPT>(x.w, a.w, b.w, __fmul_rn(h.l2, x.w), h); }
+      q = warp_sum(q);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&ss_blk[s], (double)q);
+    }
+    if (ok) {
+      if (min(min(l0, l1), min(l2_, l3)) < upto) {
+        st_stream4(v4 + i, x); st_stream4(a4 + i, a);
+        if (two) st_stream4(b4 + i, b);
+      }
+      uint32_t nl = 0;
+      if (!reset) {
+        nl = (uint32_t)max(l0, upto) | ((uint32_t)max(l1, upto) << 8) | ((uint32_t)max(l2_, upto) << 16) |
+             ((uint32_t)max(l3, upto) << 24);
+      }
+      if (nl != lw) l4[i] = nl;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < upto) ss_partials[(int64_t)threadIdx.x * n_partials + blockIdx.x] = ss_blk[threadIdx.x];
 }
 
 // scalar table / K % 4 != 0: one thread per element
@@ -220,7 +282,7 @@ __global__ void __launch_bounds__(256)
 epoch_sweep_generic_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
                            uint8_t* __restrict__ last, int64_t n_elem, int K,
                            const float* __restrict__ hyper, const float* __restrict__ lr_table, int upto,
-                           int reset, double* __restrict__ ss_partials) {
+                           int reset, double* __restrict__ ss_partials, int n_partials) {
   constexpr bool two = OptTraits<OPT>::slots == 2;
   __shared__ float lr_s[EPOCH_MAX];
   __shared__ double ss_blk[EPOCH_MAX];
@@ -255,7 +317,7 @@ epoch_sweep_generic_kernel(float* __restrict__ var, float* __restrict__ slot0, f
     if ((threadIdx.x & 31) == 0) atomicAdd(&ss_blk[s], (double)q);
   }
   __syncthreads();
-  if (threadIdx.x < upto) ss_partials[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = ss_blk[threadIdx.x];
+  if (threadIdx.x < upto) ss_partials[(int64_t)threadIdx.x * n_partials + blockIdx.x] = ss_blk[threadIdx.x];
 }
 
 // `last` of the generic sweep is updated by a separate pass (all k of a row must have read it first)
@@ -363,8 +425,18 @@ int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* la
                     int* n_partials_host, ctr_stream_t stream) {
   CTR_REQUIRE(n_rows >= 0 && K > 0 && upto >= 0 && upto <= EPOCH_MAX, CTR_ERR_INVALID_ARG,
               "ctr_epoch_sweep: bad n_rows/K/upto");
+  // tuning hook (tools/tune_epoch.py): CTR_EPOCH_CFG selects (unroll, CTAs/SM) of the K%4==0 kernel
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char* e = getenv("CTR_EPOCH_CFG");
+    cfg = e ? atoi(e) : 0;
+    if (cfg < 0 || cfg > 3) cfg = 0;
+  }
+  static const int kBlocksPerSm[4] = {3, 4, 2, 6};
   const int grid = sm_count() * 3;
-  if (n_partials_host) *n_partials_host = grid;
+  const int n_partials = sm_count() * 6;     // row length of ss_partials (>= every grid used here)
+  const int grid_v = sm_count() * kBlocksPerSm[cfg];
+  if (n_partials_host) *n_partials_host = n_partials;
   if (n_rows == 0 || upto == 0) return CTR_OK;
   CTR_REQUIRE(var && slot0 && last && hyper && lr_table && ss_partials, CTR_ERR_INVALID_ARG,
               "ctr_epoch_sweep: null buffer");
@@ -372,16 +444,31 @@ int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* la
   cudaStream_t st = as_stream(stream);
   const int64_t n_elem = n_rows * K;
   if (K % 4 == 0) {
-#define ES_CALL(OPT)                                                                                 \
-  epoch_sweep_kernel<OPT, 4, 3><<<grid, 256, 0, st>>>(var, slot0, slot1, last, n_elem / 4, K, hyper,  \
-                                                      lr_table, upto, reset, ss_partials);
+#define ES_LAUNCH(OPT, U, MB)                                                                         \
+  epoch_sweep_kernel<OPT, U, MB><<<grid_v, 256, 0, st>>>(var, slot0, slot1, last, n_elem / 4, K, hyper, \
+                                                         lr_table, upto, reset, ss_partials, n_partials)
+#define ES_CALL(OPT)                                   \
+  switch (cfg) {                                       \
+    case 1: ES_LAUNCH(OPT, 2, 4); break;               \
+    case 2: ES_LAUNCH(OPT, 4, 2); break;               \
+    case 3: ES_LAUNCH(OPT, 2, 6); break;               \
+    default: ES_LAUNCH(OPT, 4, 3); break;              \
+  }
     CTR_OPT_SWITCH(opt, ES_CALL)
 #undef ES_CALL
+#undef ES_LAUNCH
     CTR_LAUNCHED("ctr_epoch_sweep");
+  } else if (K == 1 && n_rows % 4 == 0 && ((uintptr_t)last & 3) == 0) {
+#define ES1_CALL(OPT)                                                                                \
+  epoch_sweep_k1_kernel<OPT><<<grid, 256, 0, st>>>(var, slot0, slot1, last, n_rows / 4, hyper, lr_table, \
+                                                   upto, reset, ss_partials, n_partials);
+    CTR_OPT_SWITCH(opt, ES1_CALL)
+#undef ES1_CALL
+    CTR_LAUNCHED("ctr_epoch_sweep(k1)");
   } else {
 #define ESG_CALL(OPT)                                                                                \
   epoch_sweep_generic_kernel<OPT><<<grid, 256, 0, st>>>(var, slot0, slot1, last, n_elem, K, hyper,   \
-                                                        lr_table, upto, reset, ss_partials);
+                                                        lr_table, upto, reset, ss_partials, n_partials);
     CTR_OPT_SWITCH(opt, ESG_CALL)
 #undef ESG_CALL
     CTR_LAUNCHED("ctr_epoch_sweep(generic)");

@@ -226,7 +226,7 @@ def epoch_rows(opt, apply: bool, var, slot0, slot1, last, uniq, n_uniq, g_uniq, 
 
 
 def epoch_partials_count() -> int:
-    return int(_L.ctr_device_sm_count()) * 3
+    return int(_L.ctr_device_sm_count()) * 6
 
 
 def epoch_sweep(opt, var, slot0, slot1, last, n_rows, K, hyper, lr_table, upto: int, reset: bool, ss_partials):
