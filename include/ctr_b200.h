@@ -152,7 +152,8 @@ int ctr_reduce_sum(const float* in, int64_t n, float scale, float* out, float* w
                    ctr_stream_t stream);
 /* 0.5*sum(t^2) (tf.nn.l2_loss) of a whole tensor, deterministic */
 size_t ctr_l2_loss_workspace_bytes(int64_t n);
-int ctr_l2_loss(const float* t, int64_t n, float* out, void* ws, size_t ws_bytes, ctr_stream_t stream);
+/* out[0] = scale * 0.5 * sum(t^2) */
+int ctr_l2_loss(const float* t, int64_t n, float scale, float* out, void* ws, size_t ws_bytes, ctr_stream_t stream);
 
 /* ---- K4': exact-deferred ("epoch") table update ---------------------------------------------------
  * Same results, bit for bit, as ctr_opt_sparse_rows(stage) + ctr_opt_dense_sweep + ctr_opt_patch_rows
@@ -217,6 +218,17 @@ int ctr_fc1_bwd(const float* in_a, int Ka, const float* in_b, int Kb, const floa
  * captured graph draws a fresh mask every replay.  Not TF's Philox stream. */
 int ctr_dropout_mask(float* mask, int64_t n, float keep_prob, uint64_t seed, const float* step_dev,
                      ctr_stream_t stream);
+
+/* ---- K5: DCN cross network (DCN.py:140-145) ------------------------------------------------------
+ * x_{l+1} = x0 * (x_l . w_l) + x_l + b_l,  l = 0..L-1;  w,b: [L,D];  x0: [B,D], D = F*K (D%4==0, <=2048)
+ * fwd saves the L scalars s[b,l] = x_l . w_l;  bwd recomputes x_l from x0 and s.
+ * bwd: dx0 = dx_in (NULL = 0) + dL/dx0 through the cross network;  dw, db: [L,D] (deterministic). */
+int ctr_cross_fwd(const float* x0, const float* w, const float* b, int B, int D, int L, float* xL, float* s,
+                  ctr_stream_t stream);
+size_t ctr_cross_bwd_workspace_bytes(int B, int D, int L);
+int ctr_cross_bwd(const float* x0, const float* w, const float* b, const float* s, const float* dxL,
+                  const float* dx_in, int B, int D, int L, float* dx0, float* dw, float* db, void* ws,
+                  size_t ws_bytes, ctr_stream_t stream);
 
 /* ---- table initialisation (glorot_normal_initializer, DeepFM.py:115-116; truncated at 2 sigma) --- */
 int ctr_init_trunc_normal(float* t, int64_t n, float stddev, uint64_t seed, ctr_stream_t stream);

@@ -226,8 +226,9 @@ class MLPMixin:
             d = h
         if out_scope:
             od = out_dim_in if out_dim_in is not None else d
-            self.add_param(f"{scope}/{out_scope}/weights", tfs.xavier_uniform((od, 1), gen, self.dtype))
-            self.add_param(f"{scope}/{out_scope}/biases", torch.zeros(1, dtype=self.dtype))
+            name = out_scope if "/" in out_scope else f"{scope}/{out_scope}"
+            self.add_param(f"{name}/weights", tfs.xavier_uniform((od, 1), gen, self.dtype))
+            self.add_param(f"{name}/biases", torch.zeros(1, dtype=self.dtype))
 
     def run_mlp(self, x, dense, layers, keep, train, masks, scope="Deep-part", batch_norm=False, bn_decay=0.9):
         for i in range(len(layers)):
@@ -280,3 +281,45 @@ class DeepFM(OracleModel, MLPMixin):
                                   None).reshape(-1)                                # :165-167
         y = dense["fm_bias"] * torch.ones_like(y_d) + y_w + y_v + y_d              # :172-175
         return {"y": y, "y_w": y_w, "y_v": y_v, "y_d": y_d, "x": x, "S": emb.sum(1)}
+
+
+class DCN(OracleModel, MLPMixin):
+    """DCN.py:105-230 (Deep & Cross).  No first-order term, no bias variable."""
+
+    tables = ("emb",)
+    l2_vars = ("cross_b", "cross_w", "emb")  # DCN.py:198-199, in loss order
+
+    def __init__(self, field_size, feature_size, embedding_size, deep_layers="256,128,64", cross_layers=3,
+                 dropout="0.5,0.5,0.5", batch_norm=False, batch_norm_decay=0.9, seed=0, **kw):
+        super().__init__(**kw)
+        self.F, self.N, self.K, self.L = field_size, feature_size, embedding_size, int(cross_layers)
+        self.layers, self.keep = _ints(deep_layers), _floats(dropout)
+        self.batch_norm, self.bn_decay = batch_norm, batch_norm_decay
+        self.bn_state = {}
+        D = self.F * self.K
+        gen = torch.Generator().manual_seed(seed)
+        self.add_param("cross_b", tfs.glorot_normal((self.L, D), gen, self.dtype))     # DCN.py:118-119
+        self.add_param("cross_w", tfs.glorot_normal((self.L, D), gen, self.dtype))     # :120-121
+        self.add_param("emb", tfs.glorot_normal((self.N, self.K), gen, self.dtype))    # :122-123
+        self.build_mlp(D, self.layers, gen, scope="Deep-Network", out_scope="DCN-out/out_layer",
+                       out_dim_in=D + (self.layers[-1] if self.layers else D), batch_norm=batch_norm)
+        self.init_slots()
+
+    def sites(self, batch):
+        return {"emb": ("emb", batch["feat_ids"].reshape(-1, self.F))}
+
+    def forward(self, rows, dense, batch, train, masks=None):
+        B = rows["emb"].shape[0]
+        vals = batch["feat_vals"].reshape(-1, self.F, 1).to(self.dtype)
+        x0 = (rows["emb"] * vals).reshape(B, self.F * self.K)                          # :134-138
+        xl = x0
+        for l in range(self.L):                                                        # :140-145
+            wl = dense["cross_w"][l].reshape(-1, 1)
+            xlw = xl @ wl
+            xl = x0 * xlw + xl + dense["cross_b"][l]
+        h = self.run_mlp(x0, dense, self.layers, self.keep, train, masks, scope="Deep-Network",
+                         batch_norm=self.batch_norm, bn_decay=self.bn_decay)           # :147-176
+        x_stack = torch.cat([xl, h], 1)                                                # :179
+        y = tfs.fully_connected(x_stack, dense["DCN-out/out_layer/weights"],
+                                dense["DCN-out/out_layer/biases"], None).reshape(-1)        # :180-183
+        return {"y": y, "x0": x0, "xL": xl}

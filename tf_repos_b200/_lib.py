@@ -54,7 +54,7 @@ SIGNATURES = {
     "ctr_epoch_reg_loss": (c_int, [P, P, c_int, c_int, c_float, P, c_int, P]),
     "ctr_reduce_sum": (c_int, [P, c_int64, c_float, P, P, c_size_t, P]),
     "ctr_l2_loss_workspace_bytes": (c_size_t, [c_int64]),
-    "ctr_l2_loss": (c_int, [P, c_int64, P, P, c_size_t, P]),
+    "ctr_l2_loss": (c_int, [P, c_int64, c_float, P, P, c_size_t, P]),
     "ctr_logit_loss": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P]),
     "ctr_fc_fwd": (c_int, [P, P, P, P, c_float, c_int, c_int, c_int, c_int, P, P]),
     "ctr_fc_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
@@ -63,6 +63,9 @@ SIGNATURES = {
     "ctr_fc1_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ctr_fc1_bwd": (c_int, [P, c_int, P, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
     "ctr_dropout_mask": (c_int, [P, c_int64, c_float, c_uint64, P, P]),
+    "ctr_cross_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P]),
+    "ctr_cross_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ctr_cross_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
     "ctr_init_trunc_normal": (c_int, [P, c_int64, c_float, c_uint64, P]),
     "ctr_fill": (c_int, [P, c_int64, c_float, P]),
 }

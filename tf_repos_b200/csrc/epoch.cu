@@ -429,8 +429,8 @@ int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* la
   static int cfg = -1;
   if (cfg < 0) {
     const char* e = getenv("CTR_EPOCH_CFG");
-    cfg = e ? atoi(e) : 0;
-    if (cfg < 0 || cfg > 3) cfg = 0;
+    cfg = e ? atoi(e) : 1;  // (unroll 2, 4 CTAs/SM) measured fastest on B200: profiles/
+    if (cfg < 0 || cfg > 3) cfg = 1;
   }
   static const int kBlocksPerSm[4] = {3, 4, 2, 6};
   const int grid = sm_count() * 3;

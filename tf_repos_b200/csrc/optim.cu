@@ -368,7 +368,7 @@ int ctr_reduce_sum(const float* in, int64_t n, float scale, float* out, float* w
 
 size_t ctr_l2_loss_workspace_bytes(int64_t n) { return (size_t)RED_MAX_BLOCKS * 4; }
 
-int ctr_l2_loss(const float* t, int64_t n, float* out, void* ws, size_t ws_bytes, ctr_stream_t stream) {
+int ctr_l2_loss(const float* t, int64_t n, float scale, float* out, void* ws, size_t ws_bytes, ctr_stream_t stream) {
   CTR_REQUIRE(n >= 0 && out, CTR_ERR_INVALID_ARG, "ctr_l2_loss: bad args");
   cudaStream_t st = as_stream(stream);
   const int grid = reduce_grid(n);
@@ -376,7 +376,7 @@ int ctr_l2_loss(const float* t, int64_t n, float* out, void* ws, size_t ws_bytes
   CTR_REQUIRE(n == 0 || t, CTR_ERR_INVALID_ARG, "ctr_l2_loss: null input");
   reduce_partial_kernel<true><<<grid, RED_THREADS, 0, st>>>(t, n, reinterpret_cast<float*>(ws));
   CTR_LAUNCHED("l2_partial");
-  reduce_final_kernel<<<1, RED_THREADS, 0, st>>>(reinterpret_cast<float*>(ws), grid, 0.5f, out);
+  reduce_final_kernel<<<1, RED_THREADS, 0, st>>>(reinterpret_cast<float*>(ws), grid, 0.5f * scale, out);
   CTR_LAUNCHED("l2_final");
   return CTR_OK;
 }

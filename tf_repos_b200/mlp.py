@@ -23,6 +23,8 @@ class MLP:
                  seed: int = 0):
         self.in_dim, self.layers, self.keep = in_dim, list(layers), list(keep_prob)
         self.scope, self.out_scope, self.B, self.device = scope, out_scope, B, device
+        # TF name of the output layer: "<scope>/<out_scope>", or out_scope itself when it is a full path
+        self.out_name = out_scope if (out_scope and "/" in out_scope) else f"{scope}/{out_scope}"
         self.last_dim = self.layers[-1] if self.layers else in_dim
         self.out_extra_in = out_extra_in
         self.out_in = self.last_dim + out_extra_in
@@ -46,8 +48,7 @@ class MLP:
             out += [(f"{self.scope}/mlp{i}/weights", (d, w)), (f"{self.scope}/mlp{i}/biases", (w,))]
             d = w
         if self.out_scope:
-            out += [(f"{self.scope}/{self.out_scope}/weights", (self.out_in, 1)),
-                    (f"{self.scope}/{self.out_scope}/biases", (1,))]
+            out += [(f"{self.out_name}/weights", (self.out_in, 1)), (f"{self.out_name}/biases", (1,))]
         return out
 
     def init(self, dv: DenseVars, gen: torch.Generator):
@@ -80,7 +81,7 @@ class MLP:
 
     def forward_out(self, a: torch.Tensor, dv: DenseVars, extra: Optional[torch.Tensor] = None) -> torch.Tensor:
         """y = [extra | a] @ W + b when `extra` is given (DCN: [x_L, x_deep]), else a @ W + b."""
-        W, b = dv[f"{self.scope}/{self.out_scope}/weights"], dv[f"{self.scope}/{self.out_scope}/biases"]
+        W, b = dv[f"{self.out_name}/weights"], dv[f"{self.out_name}/biases"]
         y = self.y[: a.shape[0]]
         if extra is not None:
             ops.fc1_fwd(extra, a, W.view(-1), b, y)
@@ -91,9 +92,9 @@ class MLP:
     # ---- backward ------------------------------------------------------------------------------
     def backward_out(self, a: torch.Tensor, dy: torch.Tensor, dv: DenseVars, da: torch.Tensor,
                      extra: Optional[torch.Tensor] = None):
-        W = dv[f"{self.scope}/{self.out_scope}/weights"]
-        gW = dv.grads[f"{self.scope}/{self.out_scope}/weights"].view(-1)
-        gb = dv.grads[f"{self.scope}/{self.out_scope}/biases"]
+        W = dv[f"{self.out_name}/weights"]
+        gW = dv.grads[f"{self.out_name}/weights"].view(-1)
+        gb = dv.grads[f"{self.out_name}/biases"]
         if extra is not None:
             ops.fc1_bwd(extra, a, W.view(-1), dy, self.d_extra[: a.shape[0]], da, gW, gb, self.ws)
         else:

@@ -204,6 +204,28 @@ def dropout_mask(mask, keep_prob, seed, step_dev=None):
                               _p(step_dev, torch.float32, "step"), _stream()), "ctr_dropout_mask")
 
 
+def cross_fwd(x0, w, b, xL, s):
+    B, D = x0.shape
+    L = w.shape[0]
+    check(_L.ctr_cross_fwd(_p(x0, torch.float32, "x0"), _p(w, torch.float32, "w"), _p(b, torch.float32, "b"),
+                           B, D, L, _p(xL, torch.float32, "xL"), _p(s, torch.float32, "s"), _stream()),
+          "ctr_cross_fwd")
+
+
+def cross_bwd_workspace_bytes(B, D, L) -> int:
+    return int(_L.ctr_cross_bwd_workspace_bytes(B, D, L))
+
+
+def cross_bwd(x0, w, b, s, dxL, dx_in, dx0, dw, db, ws):
+    B, D = x0.shape
+    L = w.shape[0]
+    check(_L.ctr_cross_bwd(_p(x0, torch.float32, "x0"), _p(w, torch.float32, "w"), _p(b, torch.float32, "b"),
+                           _p(s, torch.float32, "s"), _p(dxL, torch.float32, "dxL"), _p(dx_in, torch.float32, "dx_in"),
+                           B, D, L, _p(dx0, torch.float32, "dx0"), _p(dw, torch.float32, "dw"),
+                           _p(db, torch.float32, "db"), _p(ws), ws.numel() * ws.element_size(), _stream()),
+          "ctr_cross_bwd")
+
+
 def epoch_max_steps() -> int:
     return int(_L.ctr_epoch_max_steps())
 
@@ -256,10 +278,11 @@ def reduce_sum(inp, scale, out, ws):
         "ctr_reduce_sum")
 
 
-def l2_loss(t, out, ws):
+def l2_loss(t, out, ws, scale: float = 1.0):
+    """out[0] = scale * 0.5 * sum(t^2)"""
     check(
-        _L.ctr_l2_loss(_p(t, torch.float32, "t"), t.numel(), _p(out, torch.float32, "out"), _p(ws), ws.numel() * ws.element_size(),
-                       _stream()),
+        _L.ctr_l2_loss(_p(t, torch.float32, "t"), t.numel(), float(scale), _p(out, torch.float32, "out"), _p(ws),
+                       ws.numel() * ws.element_size(), _stream()),
         "ctr_l2_loss")
 
 
