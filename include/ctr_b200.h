@@ -204,10 +204,16 @@ int ctr_logit_loss(const float* bias, const float* y_a, const float* y_b, const 
  * Accumulation order is fixed => bit-reproducible. */
 int ctr_fc_fwd(const float* in, const float* Wt, const float* b, const float* drop_mask, float keep_prob,
                int M, int Kd, int Nd, int act, float* out, ctr_stream_t stream);
+/* same, plus a per-row-group bias: out = act(in@Wt + b + group_bias[row / group_P]) -- DIN's attention
+ * layer, where the ad-embedding part of [e, e-a, a] @ W is one row per sample (DIN.py:161-164) */
+int ctr_fc_fwd_grouped(const float* in, const float* Wt, const float* b, const float* group_bias, int group_P,
+                       const float* drop_mask, float keep_prob, int M, int Kd, int Nd, int act, float* out,
+                       ctr_stream_t stream);
 size_t ctr_fc_bwd_workspace_bytes(int M, int Kd, int Nd);
+/* accumulate_din != 0: dIn += dZ @ Wt^T (instead of =) */
 int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* drop_mask, float keep_prob,
-               float* dOut, int M, int Kd, int Nd, int act, float* dIn, float* dW, float* db, void* ws,
-               size_t ws_bytes, ctr_stream_t stream);
+               float* dOut, int M, int Kd, int Nd, int act, float* dIn, int accumulate_din, float* dW, float* db,
+               void* ws, size_t ws_bytes, ctr_stream_t stream);
 int ctr_fc1_fwd(const float* in_a, int Ka, const float* in_b, int Kb, const float* w, const float* b, int M,
                 float* y, ctr_stream_t stream);
 size_t ctr_fc1_bwd_workspace_bytes(int M, int Ka, int Kb);
@@ -229,6 +235,32 @@ size_t ctr_cross_bwd_workspace_bytes(int B, int D, int L);
 int ctr_cross_bwd(const float* x0, const float* w, const float* b, const float* s, const float* dxL,
                   const float* dx_in, int B, int D, int L, float* dx0, float* dw, float* db, void* ws,
                   size_t ws_bytes, ctr_stream_t stream);
+
+/* ---- K6/K9: DIN embedding + field-wise pooling layers (DIN.py:143-183) ---------------------------
+ * gather_scale_rows: out[(i/G)*ld_group + (i%G)*K + k] = V[ids[i]][k] * (wgt ? wgt[i] : 1)
+ *     (tf.nn.embedding_lookup of feat_ids / a_catids / padded behaviour ids, DIN.py:143-147,155-156;
+ *      G, ld_group let the rows land directly inside the concatenated MLP input, DIN.py:199)
+ * bag_sum: tf.nn.embedding_lookup_sparse(combiner="sum") over CSR bags (a_intids, DIN.py:148; the
+ *     non-attention pooling branch :180-183) and its gradient g_rows[i] = d_out[bag(i)] * w_i
+ * din_pool: att = sigmoid(z); u[b] = sum_p (ids[b,p] > 0) * att[b,p] * E[b,p,:]   (DIN.py:169-172)
+ *     bwd: dE = mask*att*du (written, not accumulated); dz = mask*att*(1-att)*(E . du)
+ * group_sum: dU[b] = sum_p dZ[b*P+p]   (gradient of ctr_fc_fwd_grouped's group bias)
+ * scale_rows: out[i,:] = (x[(i/G)*ld_group + (i%G)*K : +K] + add[i,:]) * w[i]  (add, w optional)
+ * axpby: out = alpha*a + beta*b */
+int ctr_gather_scale_rows(const int32_t* ids, const float* wgt, const float* V, int64_t N, int64_t n, int K,
+                          int G, int64_t ld_group, float* out, int32_t* oob, ctr_stream_t stream);
+int ctr_bag_sum_fwd(const int32_t* ids, const float* wgt, const int32_t* offsets, const float* V, int64_t N,
+                    int B, int K, int64_t ld, float* out, ctr_stream_t stream);
+int ctr_bag_sum_bwd(const float* d_out, int64_t ld, const float* wgt, const int32_t* offsets, int B, int K,
+                    float* g_rows, ctr_stream_t stream);
+int ctr_scale_rows(const float* x, const float* add, const float* w, int64_t n, int K, int G, int64_t ld_group,
+                   float* out, ctr_stream_t stream);
+int ctr_din_pool_fwd(const float* E, const float* z, const int32_t* ids, int B, int P, int K, float* att, float* u,
+                     int64_t ld_u, ctr_stream_t stream);
+int ctr_din_pool_bwd(const float* E, const float* att, const int32_t* ids, const float* du, int64_t ld_u, int B,
+                     int P, int K, float* dE, float* dz, ctr_stream_t stream);
+int ctr_group_sum(const float* dZ, int B, int P, int N, float* dU, ctr_stream_t stream);
+int ctr_axpby(const float* a, float alpha, const float* b, float beta, int64_t n, float* out, ctr_stream_t stream);
 
 /* ---- table initialisation (glorot_normal_initializer, DeepFM.py:115-116; truncated at 2 sigma) --- */
 int ctr_init_trunc_normal(float* t, int64_t n, float stddev, uint64_t seed, ctr_stream_t stream);

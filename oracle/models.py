@@ -323,3 +323,81 @@ class DCN(OracleModel, MLPMixin):
         y = tfs.fully_connected(x_stack, dense["DCN-out/out_layer/weights"],
                                 dense["DCN-out/out_layer/biases"], None).reshape(-1)        # :180-183
         return {"y": y, "x0": x0, "xL": xl}
+
+
+class DIN(OracleModel, MLPMixin):
+    """DIN.py:101-257.  batch keys: feat_ids [B,F'], a_ids [3,B], a_int_ids [nnz] + a_int_off [B+1],
+    u_ids [4,B,P] / u_wgt [4,B,P] (0-padded, as sparse_tensor_to_dense produces, DIN.py:153-154)."""
+
+    tables = ("embeddings",)
+    l2_vars = ("embeddings",)  # DIN.py:226
+    ATT = "Field-wise-Pooling-layer"
+
+    def __init__(self, field_size, feature_size, embedding_size, deep_layers="256,128,64", dropout="0.5,0.5,0.5",
+                 attention_layers="256", attention_pooling=True, seed=0, **kw):
+        super().__init__(**kw)
+        self.Fp, self.N, self.K = field_size, feature_size, embedding_size
+        self.layers, self.keep = _ints(deep_layers), _floats(dropout)
+        self.att_layers = _ints(attention_layers)
+        self.attention_pooling = attention_pooling
+        self.bn_state = {}
+        K = self.K
+        gen = torch.Generator().manual_seed(seed)
+        self.add_param("embeddings", tfs.glorot_normal((self.N, K), gen, self.dtype))     # DIN.py:115
+        if attention_pooling:
+            d = 3 * K
+            for i in range(len(self.att_layers)):                                        # widths = layers[i] (Q5)
+                self.add_param(f"{self.ATT}/att_fc{i}/weights", tfs.xavier_uniform((d, self.layers[i]), gen, self.dtype))
+                self.add_param(f"{self.ATT}/att_fc{i}/biases", torch.zeros(self.layers[i], dtype=self.dtype))
+                d = self.layers[i]
+            self.add_param(f"{self.ATT}/att_out/weights", tfs.xavier_uniform((d, 1), gen, self.dtype))
+            self.add_param(f"{self.ATT}/att_out/biases", torch.zeros(1, dtype=self.dtype))
+        self.build_mlp(self.Fp * K + 8 * K, self.layers, gen, scope="MLP-layer", out_scope="DIN-out/din_out")
+        self.init_slots()
+
+    def sites(self, batch):
+        s = {"common": ("embeddings", batch["feat_ids"]),
+             "a_cat": ("embeddings", batch["a_ids"][0]), "a_shop": ("embeddings", batch["a_ids"][1]),
+             "a_brand": ("embeddings", batch["a_ids"][2]), "a_int": ("embeddings", batch["a_int_ids"])}
+        for f, nm in enumerate(("cat", "shop", "brand", "int")):
+            s[f"u_{nm}"] = ("embeddings", batch["u_ids"][f])
+        return s
+
+    def _attention_unit(self, dense_emb_raw, ids, wgt, a_emb, dense, train, masks, f):
+        K = self.K
+        B, P = ids.shape
+        dense_emb = dense_emb_raw * wgt.unsqueeze(-1).to(self.dtype)                      # :155-156
+        mask = (ids > 0).to(self.dtype).unsqueeze(-1)                                     # :157
+        ub = dense_emb.reshape(-1, K)
+        ax = a_emb.repeat(1, P).reshape(-1, K)                                            # :160-161
+        x = torch.cat([ub, ub - ax, ax], 1)                                               # :162
+        for i in range(len(self.att_layers)):
+            x = tfs.fully_connected(x, dense[f"{self.ATT}/att_fc{i}/weights"], dense[f"{self.ATT}/att_fc{i}/biases"], "relu")
+            if train:
+                m = None if masks is None or masks.get("att") is None else masks["att"][f]
+                x = tfs.dropout(x, self.keep[i], m)                                       # :167-168
+        att = tfs.fully_connected(x, dense[f"{self.ATT}/att_out/weights"], dense[f"{self.ATT}/att_out/biases"], "sigmoid")
+        att = att.reshape(B, P, 1)                                                        # :169-170
+        return ((dense_emb * att) * mask).sum(1)                                          # :171-172
+
+    def forward(self, rows, dense, batch, train, masks=None):
+        K = self.K
+        B = batch["feat_ids"].shape[0]
+        common = rows["common"].reshape(B, self.Fp * K)
+        a = [rows["a_cat"], rows["a_shop"], rows["a_brand"]]
+        off = batch["a_int_off"].long()
+        seg = torch.repeat_interleave(torch.arange(B), off[1:] - off[:-1])
+        a_int = torch.zeros(B, K, dtype=self.dtype).index_add(0, seg, rows["a_int"])       # :148 (sum combiner)
+        a.append(a_int)
+        u = []
+        for f, nm in enumerate(("cat", "shop", "brand", "int")):
+            ids, wgt = batch["u_ids"][f], batch["u_wgt"][f]
+            if self.attention_pooling:
+                u.append(self._attention_unit(rows[f"u_{nm}"], ids, wgt, a[f], dense, train, masks, f))
+            else:
+                u.append((rows[f"u_{nm}"] * wgt.unsqueeze(-1).to(self.dtype)).sum(1))      # :180-183
+        x = torch.cat([common] + u + a, 1)                                                 # :199
+        mm = None if masks is None else masks.get("mlp")
+        h = self.run_mlp(x, dense, self.layers, self.keep, train, mm, scope="MLP-layer")
+        y = tfs.fully_connected(h, dense["DIN-out/din_out/weights"], dense["DIN-out/din_out/biases"], None).reshape(-1)
+        return {"y": y, "x": x}

@@ -58,7 +58,8 @@ SIGNATURES = {
     "ctr_logit_loss": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P]),
     "ctr_fc_fwd": (c_int, [P, P, P, P, c_float, c_int, c_int, c_int, c_int, P, P]),
     "ctr_fc_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "ctr_fc_bwd": (c_int, [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "ctr_fc_fwd_grouped": (c_int, [P, P, P, P, c_int, P, c_float, c_int, c_int, c_int, c_int, P, P]),
+    "ctr_fc_bwd": (c_int, [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, P, c_int, P, P, P, c_size_t, P]),
     "ctr_fc1_fwd": (c_int, [P, c_int, P, c_int, P, P, c_int, P, P]),
     "ctr_fc1_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ctr_fc1_bwd": (c_int, [P, c_int, P, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
@@ -66,6 +67,14 @@ SIGNATURES = {
     "ctr_cross_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P]),
     "ctr_cross_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ctr_cross_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "ctr_gather_scale_rows": (c_int, [P, P, P, c_int64, c_int64, c_int, c_int, c_int64, P, P, P]),
+    "ctr_bag_sum_fwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int64, P, P]),
+    "ctr_bag_sum_bwd": (c_int, [P, c_int64, P, P, c_int, c_int, P, P]),
+    "ctr_scale_rows": (c_int, [P, P, P, c_int64, c_int, c_int, c_int64, P, P]),
+    "ctr_din_pool_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int64, P]),
+    "ctr_din_pool_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P]),
+    "ctr_group_sum": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "ctr_axpby": (c_int, [P, c_float, P, c_float, c_int64, P, P]),
     "ctr_init_trunc_normal": (c_int, [P, c_int64, c_float, c_uint64, P]),
     "ctr_fill": (c_int, [P, c_int64, c_float, P]),
 }

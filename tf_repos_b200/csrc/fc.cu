@@ -20,12 +20,15 @@ constexpr int GEMM_BK = 16;
 //   A_RC (reduce-contiguous): A(i,r) = A[i*lda + r]   else  A(i,r) = A[r*lda + i]
 //   B_RC (reduce-contiguous): B(r,j) = B[j*ldb + r]   else  B(r,j) = B[r*ldb + j]
 // blockIdx.z splits R into gridDim.z chunks; chunk z writes C + z*M*N (EPI 0) .
-// EPI 1: C = act(acc + bias[j]) (/keep * mask[i][j])    (act: 0 identity, 1 relu)
+// EPI 1: C = act(acc + bias[j] + gbias[i / gP][j]) (/keep * mask[i][j])   (act: 0 identity, 1 relu)
+//        gbias: optional per-row-group bias (DIN: one row per sample, shared by its P positions)
+// EPI 2: C += acc
 template <int BM, int BN, int TM, int TN, bool A_RC, bool B_RC, int EPI>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_tile_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                  float* __restrict__ C, int ldc, int M, int N, int R, const float* __restrict__ bias,
-                 int act, const float* __restrict__ mask, float keep) {
+                 int act, const float* __restrict__ mask, float keep, const float* __restrict__ gbias,
+                 int gP) {
   constexpr int NT = (BM / TM) * (BN / TN);
   __shared__ __align__(16) float As[2][GEMM_BK][BM + 4];
   __shared__ __align__(16) float Bs[2][GEMM_BK][BN + 4];
@@ -99,8 +102,10 @@ gemm_tile_kernel(const float* __restrict__ A, int lda, const float* __restrict__
       const int gj = j0 + tx * TN + w;
       if (gj >= N) continue;
       float v = acc[u][w];
+      if (EPI == 2) v += Cz[(int64_t)gi * ldc + gj];
       if (EPI == 1) {
         if (bias) v += bias[gj];
+        if (gbias) v += gbias[(int64_t)(gi / gP) * N + gj];
         if (act == 1) v = fmaxf(v, 0.f);
         if (mask) v = __fdiv_rn(v, keep) * mask[(int64_t)gi * ldc + gj];  // tf.nn.dropout: x/keep*binary
       }
@@ -237,9 +242,20 @@ using namespace ctr;
 
 extern "C" {
 
+int ctr_fc_fwd_grouped(const float* in, const float* Wt, const float* b, const float* group_bias, int group_P,
+                       const float* drop_mask, float keep_prob, int M, int Kd, int Nd, int act, float* out,
+                       ctr_stream_t stream);
+
 int ctr_fc_fwd(const float* in, const float* Wt, const float* b, const float* drop_mask, float keep_prob,
                int M, int Kd, int Nd, int act, float* out, ctr_stream_t stream) {
-  CTR_REQUIRE(M >= 0 && Kd > 0 && Nd > 0 && (act == 0 || act == 1), CTR_ERR_INVALID_ARG, "ctr_fc_fwd: bad shape/act");
+  return ctr_fc_fwd_grouped(in, Wt, b, nullptr, 1, drop_mask, keep_prob, M, Kd, Nd, act, out, stream);
+}
+
+int ctr_fc_fwd_grouped(const float* in, const float* Wt, const float* b, const float* group_bias, int group_P,
+                       const float* drop_mask, float keep_prob, int M, int Kd, int Nd, int act, float* out,
+                       ctr_stream_t stream) {
+  CTR_REQUIRE(M >= 0 && Kd > 0 && Nd > 0 && (act == 0 || act == 1) && group_P >= 1, CTR_ERR_INVALID_ARG,
+              "ctr_fc_fwd: bad shape/act");
   if (M == 0) return CTR_OK;
   CTR_REQUIRE(in && Wt && out, CTR_ERR_INVALID_ARG, "ctr_fc_fwd: null buffer");
   CTR_REQUIRE(!drop_mask || keep_prob > 0.f, CTR_ERR_INVALID_ARG, "ctr_fc_fwd: keep_prob must be > 0");
@@ -247,11 +263,11 @@ int ctr_fc_fwd(const float* in, const float* Wt, const float* b, const float* dr
   if (Nd >= 128) {
     dim3 grid((Nd + 127) / 128, (M + 63) / 64, 1);
     gemm_tile_kernel<64, 128, 4, 8, true, false, 1><<<grid, 256, 0, st>>>(in, Kd, Wt, Nd, out, Nd, M, Nd, Kd, b, act,
-                                                                          drop_mask, keep_prob);
+                                                                          drop_mask, keep_prob, group_bias, group_P);
   } else {
     dim3 grid((Nd + 63) / 64, (M + 63) / 64, 1);
     gemm_tile_kernel<64, 64, 4, 4, true, false, 1><<<grid, 256, 0, st>>>(in, Kd, Wt, Nd, out, Nd, M, Nd, Kd, b, act,
-                                                                         drop_mask, keep_prob);
+                                                                         drop_mask, keep_prob, group_bias, group_P);
   }
   CTR_LAUNCHED("ctr_fc_fwd");
   return CTR_OK;
@@ -265,8 +281,8 @@ size_t ctr_fc_bwd_workspace_bytes(int M, int Kd, int Nd) {
 }
 
 int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* drop_mask, float keep_prob,
-               float* dOut, int M, int Kd, int Nd, int act, float* dIn, float* dW, float* db, void* ws,
-               size_t ws_bytes, ctr_stream_t stream) {
+               float* dOut, int M, int Kd, int Nd, int act, float* dIn, int accumulate_din, float* dW, float* db,
+               void* ws, size_t ws_bytes, ctr_stream_t stream) {
   CTR_REQUIRE(M >= 0 && Kd > 0 && Nd > 0 && (act == 0 || act == 1), CTR_ERR_INVALID_ARG, "ctr_fc_bwd: bad shape/act");
   if (M == 0) return CTR_OK;
   CTR_REQUIRE(in && Wt && out && dOut && dW && db, CTR_ERR_INVALID_ARG, "ctr_fc_bwd: null buffer");
@@ -286,7 +302,7 @@ int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* 
   {
     dim3 grid((Nd + 63) / 64, (Kd + 63) / 64, S);
     gemm_tile_kernel<64, 64, 4, 4, false, false, 0><<<grid, 256, 0, st>>>(in, Kd, dOut, Nd, S == 1 ? dW : dw_part, Nd,
-                                                                          Kd, Nd, M, nullptr, 0, nullptr, 1.f);
+                                                                          Kd, Nd, M, nullptr, 0, nullptr, 1.f, nullptr, 1);
     CTR_LAUNCHED("fc_dw");
     if (S > 1) {
       const int64_t n = (int64_t)Kd * Nd;
@@ -297,8 +313,12 @@ int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* 
   // 3. dIn[M,Kd] = dZ @ W^T
   if (dIn) {
     dim3 grid((Kd + 127) / 128, (M + 63) / 64, 1);
-    gemm_tile_kernel<64, 128, 4, 8, true, true, 0><<<grid, 256, 0, st>>>(dOut, Nd, Wt, Nd, dIn, Kd, M, Kd, Nd, nullptr, 0,
-                                                                         nullptr, 1.f);
+    if (accumulate_din)
+      gemm_tile_kernel<64, 128, 4, 8, true, true, 2><<<grid, 256, 0, st>>>(dOut, Nd, Wt, Nd, dIn, Kd, M, Kd, Nd, nullptr,
+                                                                           0, nullptr, 1.f, nullptr, 1);
+    else
+      gemm_tile_kernel<64, 128, 4, 8, true, true, 0><<<grid, 256, 0, st>>>(dOut, Nd, Wt, Nd, dIn, Kd, M, Kd, Nd, nullptr,
+                                                                           0, nullptr, 1.f, nullptr, 1);
     CTR_LAUNCHED("fc_din");
   }
   return CTR_OK;

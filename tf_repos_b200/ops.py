@@ -169,12 +169,21 @@ def fc_bwd_workspace_bytes(M, Kd, Nd) -> int:
     return int(_L.ctr_fc_bwd_workspace_bytes(M, Kd, Nd))
 
 
-def fc_bwd(inp, Wt, out, drop_mask, keep_prob, dOut, act, dIn, dW, db, ws):
+def fc_fwd_grouped(inp, Wt, b, group_bias, group_P, drop_mask, keep_prob, act, out):
+    M, Kd = inp.shape
+    Nd = Wt.shape[1]
+    check(_L.ctr_fc_fwd_grouped(_p(inp, torch.float32, "in"), _p(Wt, torch.float32, "Wt"), _p(b, torch.float32, "b"),
+                                _p(group_bias, torch.float32, "group_bias"), group_P,
+                                _p(drop_mask, torch.float32, "drop_mask"), float(keep_prob), M, Kd, Nd, act,
+                                _p(out, torch.float32, "out"), _stream()), "ctr_fc_fwd_grouped")
+
+
+def fc_bwd(inp, Wt, out, drop_mask, keep_prob, dOut, act, dIn, dW, db, ws, accumulate_din=False):
     M, Kd = inp.shape
     Nd = Wt.shape[1]
     check(_L.ctr_fc_bwd(_p(inp, torch.float32, "in"), _p(Wt, torch.float32, "Wt"), _p(out, torch.float32, "out"),
                         _p(drop_mask, torch.float32, "drop_mask"), float(keep_prob), _p(dOut, torch.float32, "dOut"),
-                        M, Kd, Nd, act, _p(dIn, torch.float32, "dIn"), _p(dW, torch.float32, "dW"),
+                        M, Kd, Nd, act, _p(dIn, torch.float32, "dIn"), int(accumulate_din), _p(dW, torch.float32, "dW"),
                         _p(db, torch.float32, "db"), _p(ws), ws.numel() * ws.element_size(), _stream()), "ctr_fc_bwd")
 
 
@@ -224,6 +233,63 @@ def cross_bwd(x0, w, b, s, dxL, dx_in, dx0, dw, db, ws):
                            B, D, L, _p(dx0, torch.float32, "dx0"), _p(dw, torch.float32, "dw"),
                            _p(db, torch.float32, "db"), _p(ws), ws.numel() * ws.element_size(), _stream()),
           "ctr_cross_bwd")
+
+
+def _dptr(t: torch.Tensor) -> int:
+    """device pointer of a (possibly strided / offset) view; only the base address is used"""
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise CtrError("expected a CUDA float32 tensor")
+    return t.data_ptr()
+
+
+def gather_scale_rows(ids, wgt, V, out_view, G, ld_group, oob=None):
+    """out_view: tensor VIEW whose data_ptr is the first output element (e.g. x_deep[:, off:])"""
+    N, K = V.shape
+    check(_L.ctr_gather_scale_rows(_p(ids, torch.int32, "ids"), _p(wgt, torch.float32, "wgt"), _p(V, torch.float32, "V"),
+                                   N, ids.numel(), K, G, ld_group, _dptr(out_view), _p(oob, torch.int32, "oob"),
+                                   _stream()), "ctr_gather_scale_rows")
+
+
+def bag_sum_fwd(ids, wgt, offsets, V, out_view, ld):
+    N, K = V.shape
+    B = offsets.numel() - 1
+    check(_L.ctr_bag_sum_fwd(_p(ids, torch.int32, "ids"), _p(wgt, torch.float32, "wgt"),
+                             _p(offsets, torch.int32, "offsets"), _p(V, torch.float32, "V"), N, B, K, ld,
+                             _dptr(out_view), _stream()), "ctr_bag_sum_fwd")
+
+
+def bag_sum_bwd(d_out_view, ld, wgt, offsets, K, g_rows):
+    B = offsets.numel() - 1
+    check(_L.ctr_bag_sum_bwd(_dptr(d_out_view), ld, _p(wgt, torch.float32, "wgt"), _p(offsets, torch.int32, "offsets"),
+                             B, K, _p(g_rows, torch.float32, "g_rows"), _stream()), "ctr_bag_sum_bwd")
+
+
+def scale_rows(x_view, add, w, n, K, G, ld_group, out):
+    """out[i] = (x_view[(i/G)*ld_group + (i%G)*K : +K] + add[i]) * w[i]   (add, w optional)"""
+    check(_L.ctr_scale_rows(_dptr(x_view), _p(add, torch.float32, "add"), _p(w, torch.float32, "w"), n, K, G, ld_group,
+                            _dptr(out), _stream()), "ctr_scale_rows")
+
+
+def din_pool_fwd(E, z, ids, B, P, K, att, u_view, ld_u):
+    check(_L.ctr_din_pool_fwd(_p(E, torch.float32, "E"), _p(z, torch.float32, "z"), _p(ids, torch.int32, "ids"),
+                              B, P, K, _p(att, torch.float32, "att"), _dptr(u_view), ld_u, _stream()),
+          "ctr_din_pool_fwd")
+
+
+def din_pool_bwd(E, att, ids, du_view, ld_u, B, P, K, dE, dz):
+    check(_L.ctr_din_pool_bwd(_p(E, torch.float32, "E"), _p(att, torch.float32, "att"), _p(ids, torch.int32, "ids"),
+                              _dptr(du_view), ld_u, B, P, K, _p(dE, torch.float32, "dE"), _p(dz, torch.float32, "dz"),
+                              _stream()), "ctr_din_pool_bwd")
+
+
+def group_sum(dZ, B, P, N, dU):
+    check(_L.ctr_group_sum(_p(dZ, torch.float32, "dZ"), B, P, N, _p(dU, torch.float32, "dU"), _stream()),
+          "ctr_group_sum")
+
+
+def axpby(a, alpha, b, beta, out):
+    check(_L.ctr_axpby(_p(a, torch.float32, "a"), float(alpha), _p(b, torch.float32, "b"), float(beta), a.numel(),
+                       _p(out, torch.float32, "out"), _stream()), "ctr_axpby")
 
 
 def epoch_max_steps() -> int:

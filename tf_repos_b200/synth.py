@@ -47,3 +47,29 @@ def write_libsvm(path: str, ids, vals, labels):
             toks += ["%d:%s" % (int(i), ("%.6f" % v).rstrip("0").rstrip(".") if v != 1.0 else "1")
                      for i, v in zip(ids[b], vals[b])]
             fo.write(" ".join(toks) + "\n")
+
+
+def din_batch(B: int, N: int, Fp: int = 11, P: int = 100, max_a_int: int = 8, seed: int = 0, device="cpu",
+              fixed_len: bool = False):
+    """Synthetic DIN batch with the feature names/shapes of DIN.py:60-77 (Ali-CCP layout): ids uniform in
+    [1, N) (0 = padding sentinel), behaviour lengths ~ U{1..P} (or all P), weights ~ U(0,3), a_int bags of
+    1..max_a_int ids; label ~ Bernoulli(0.25).  """
+    g = torch.Generator().manual_seed(seed)
+    ri = lambda *shape: torch.randint(1, N, shape, generator=g, dtype=torch.int64).to(torch.int32)
+    feat_ids = ri(B, Fp)
+    a_ids = ri(3, B)
+    lens_a = torch.randint(1, max_a_int + 1, (B,), generator=g)
+    a_off = torch.zeros(B + 1, dtype=torch.int32)
+    a_off[1:] = torch.cumsum(lens_a, 0).to(torch.int32)
+    a_int_ids = ri(int(a_off[-1]))
+    u_ids = ri(4, B, P)
+    u_wgt = torch.rand(4, B, P, generator=g) * 3.0
+    if not fixed_len:
+        lens = torch.randint(1, P + 1, (4, B), generator=g)
+        pad = torch.arange(P).view(1, 1, P) >= lens.unsqueeze(-1)
+        u_ids[pad] = 0
+        u_wgt[pad] = 0.0
+    labels = (torch.rand(B, generator=g) < 0.25).float()
+    batch = {"feat_ids": feat_ids, "a_ids": a_ids, "a_int_ids": a_int_ids, "a_int_off": a_off,
+             "u_ids": u_ids, "u_wgt": u_wgt}
+    return {k: v.to(device) for k, v in batch.items()}, labels.to(device)
