@@ -82,8 +82,14 @@ def sigmoid(x: torch.Tensor) -> torch.Tensor:
 
 def sigmoid_cross_entropy_with_logits(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     """tf.nn.sigmoid_cross_entropy_with_logits (DeepFM.py:188) [TF-sem]:
-    max(x,0) - x*z + log(1+exp(-|x|))."""
-    return torch.clamp(logits, min=0) - logits * labels + torch.log1p(torch.exp(-logits.abs()))
+    max(x,0) - x*z + log(1+exp(-|x|)), written with tf.where(x >= 0, ...) selects exactly like TF's
+    nn_impl.py so that autodiff at x == 0 gives sigmoid(0) - z (clamp/abs would give the subgradient
+    -z there; logits are exactly 0 whenever every relu of the last hidden layer is dead)."""
+    zeros = torch.zeros_like(logits)
+    cond = logits >= zeros
+    relu_logits = torch.where(cond, logits, zeros)
+    neg_abs_logits = torch.where(cond, -logits, logits)
+    return relu_logits - logits * labels + torch.log1p(torch.exp(neg_abs_logits))
 
 
 def fully_connected(x, W, b, activation: Optional[str] = "relu"):
