@@ -262,6 +262,14 @@ int ctr_din_pool_bwd(const float* E, const float* att, const int32_t* ids, const
 int ctr_group_sum(const float* dZ, int B, int P, int N, float* dU, ctr_stream_t stream);
 int ctr_axpby(const float* a, float alpha, const float* b, float beta, int64_t n, float* out, ctr_stream_t stream);
 
+/* ---- libsvm input (HOST buffers) -------------------------------------------------------------------
+ * decode_libsvm of input_fn (DeepFM.py:65-81): "<label> <id>:<val> ..." lines -> ids int32 [rows,F],
+ * vals f32 [rows,F], labels f32 [rows].  Parses complete lines of buf_host[0,len) up to max_rows;
+ * returns rows parsed (or <0), *consumed_host = bytes consumed.  All pointers are HOST pointers. */
+int64_t ctr_parse_libsvm(const char* buf_host, size_t len, int F, int64_t max_rows, int final_chunk,
+                         int32_t* ids_host, float* vals_host, float* labels_host, size_t* consumed_host);
+int ctr_libsvm_count_fields(const char* buf_host, size_t len);
+
 /* ---- table initialisation (glorot_normal_initializer, DeepFM.py:115-116; truncated at 2 sigma) --- */
 int ctr_init_trunc_normal(float* t, int64_t n, float stddev, uint64_t seed, ctr_stream_t stream);
 int ctr_fill(float* t, int64_t n, float value, ctr_stream_t stream);

@@ -150,7 +150,8 @@ class CTRModel:
         {mean CE, l2*l2_loss terms in the order of the reference's loss expression} whose left-to-right
         sum is `loss` (table terms come from the dense sweep in exact mode; zeros otherwise)."""
         B, F, K = ids.shape[0], self.F, self.K
-        assert B == self.B, "train_step is specialised for the configured batch size"
+        assert B <= self.B, "batch larger than the configured batch_size"
+        assert B == self.B or self.world == 1, "partial batches are not supported under data parallelism"
         deferred = self.update_mode == "exact_deferred"
         upd = self.updater
         if deferred:
@@ -169,17 +170,19 @@ class CTRModel:
         else:
             self.opt.tick()
         bias, y_a, y_b, y_c = self._forward(ids, vals, train=True, masks=masks)
-        ops.logit_loss(bias, y_a, y_b, y_c, labels, B, y=self.y, pred=self.pred, loss_ce=self.loss_ce, dy=self.dy,
-                       dbias=(self.dense.grads[self.bias_name] if self.bias_name else None), B_total=B * self.world)
+        ops.logit_loss(bias, y_a, y_b, y_c, labels, B, y=self.y[:B], pred=self.pred[:B], loss_ce=self.loss_ce,
+                       dy=self.dy[:B], dbias=(self.dense.grads[self.bias_name] if self.bias_name else None),
+                       B_total=B * self.world)
         self._backward(ids, vals)
-        g_rows, g_w = self.g_rows, self.g_w
+        g_rows = self.g_rows[: B * F]
+        g_w = self.g_w[: B * F] if self.g_w is not None else None
         if self.world > 1:
             import torch.distributed as dist
             if not deferred:
                 dist.all_gather_into_tensor(self.ids_all, ids.reshape(-1))
-            dist.all_gather_into_tensor(self.g_rows_all, self.g_rows)
+            dist.all_gather_into_tensor(self.g_rows_all, g_rows)
             if g_w is not None:
-                dist.all_gather_into_tensor(self.g_w_all, self.g_w)
+                dist.all_gather_into_tensor(self.g_w_all, g_w)
             dist.all_reduce(self.dense.grad)  # dense gradients + the loss tail, summed over ranks
             g_rows, g_w = self.g_rows_all, (self.g_w_all if g_w is not None else None)
         if deferred:

@@ -65,17 +65,15 @@ class DCN(CTRModel):
         return None, y, None, None
 
     def _backward(self, ids, vals):
-        B = self.B
-        xl = self.xL if self.L > 0 else self.x0
-        self.mlp.backward_out(self._a, self.dy, self.dense, self.d_h, extra=xl)    # d x_L -> mlp.d_extra, d x_deep -> d_h
-        dX = self.mlp.backward_hidden(self.x0, self.d_h, self.dense)               # d x0 through the deep network
-        if self.L > 0:
-            ops.cross_bwd(self.x0, self.dense["cross_w"], self.dense["cross_b"], self.s, self.mlp.d_extra, dX,
-                          self.dx, self.dense.grads["cross_w"], self.dense.grads["cross_b"], self.cross_ws)
-            dX = self.dx
-        else:
+        B = ids.shape[0]
+        if self.L <= 0:
             raise NotImplementedError("cross_layers == 0 (the reference's flag default is 3)")
-        ops.fm_embed_bwd(vals, None, None, dX, None, None, self.K, ops.FM_PLAIN, self.g_rows, None)
+        dy = self.dy[:B]
+        self.mlp.backward_out(self._a, dy, self.dense, self.d_h[:B], extra=self.xL[:B])  # d x_L -> mlp.d_extra, d x_deep -> d_h
+        dX = self.mlp.backward_hidden(self.x0[:B], self.d_h[:B], self.dense)             # d x0 through the deep network
+        ops.cross_bwd(self.x0[:B], self.dense["cross_w"], self.dense["cross_b"], self.s[:B], self.mlp.d_extra[:B], dX,
+                      self.dx[:B], self.dense.grads["cross_w"], self.dense.grads["cross_b"], self.cross_ws)
+        ops.fm_embed_bwd(vals, None, None, self.dx[:B], None, None, self.K, ops.FM_PLAIN, self.g_rows[: B * self.F], None)
 
     def _dense_reg_terms(self):
         # loss = CE + l2*l2_loss(cross_b) + l2*l2_loss(cross_w) + l2*l2_loss(emb)   (DCN.py:198-199)

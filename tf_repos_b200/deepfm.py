@@ -50,6 +50,9 @@ class DeepFM(CTRModel):
         return self.dense["fm_bias"], self.y_w[:B], self.y_v[:B], y_d                       # :172-175
 
     def _backward(self, ids, vals):
-        self.mlp.backward_out(self._a, self.dy, self.dense, self.d_last)
-        dX = self.mlp.backward_hidden(self.x, self.d_last, self.dense)
-        ops.fm_embed_bwd(vals, self.x, self.S, dX, self.dy, self.dy, self.K, ops.FM_DEEPFM, self.g_rows, self.g_w)
+        B = ids.shape[0]
+        dy = self.dy[:B]
+        self.mlp.backward_out(self._a, dy, self.dense, self.d_last[:B])
+        dX = self.mlp.backward_hidden(self.x[:B], self.d_last[:B], self.dense)
+        ops.fm_embed_bwd(vals, self.x[:B], self.S[:B], dX, dy, dy, self.K, ops.FM_DEEPFM,
+                         self.g_rows[: B * self.F], self.g_w[: B * self.F])

@@ -90,8 +90,9 @@ class UniqueWorkspace:
 
 def unique_segment(ids_flat: torch.Tensor, uw: UniqueWorkspace) -> None:
     n = ids_flat.numel()
-    if n != uw.n:
-        raise CtrError(f"workspace was sized for n={uw.n}, got {n}")
+    if n > uw.n:
+        raise CtrError(f"workspace was sized for n<={uw.n}, got {n}")
+    uw.n_active = n   # a final partial batch (DeepFM.py:88-90 keeps it) has fewer ids than the capacity
     check(
         _L.ctr_unique_segment(
             _p(ids_flat, torch.int32, "ids"), n, uw.N, _p(uw.perm), _p(uw.uniq), _p(uw.inverse),
@@ -103,7 +104,7 @@ def segment_sum_rows(g_rows, g_w, uw: UniqueWorkspace, K, g_uniq, gw_uniq=None):
     check(
         _L.ctr_segment_sum_rows(
             _p(g_rows, torch.float32, "g_rows"), _p(g_w, torch.float32, "g_w"), _p(uw.perm),
-            _p(uw.seg_offsets), _p(uw.n_uniq), _p(uw.long_list), uw.n, K,
+            _p(uw.seg_offsets), _p(uw.n_uniq), _p(uw.long_list), getattr(uw, "n_active", uw.n), K,
             _p(g_uniq, torch.float32, "g_uniq"), _p(gw_uniq, torch.float32, "gw_uniq"), _stream()),
         "ctr_segment_sum_rows")
 
