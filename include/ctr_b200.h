@@ -262,6 +262,26 @@ int ctr_din_pool_bwd(const float* E, const float* att, const int32_t* ids, const
 int ctr_group_sum(const float* dZ, int B, int P, int N, float* dU, ctr_stream_t stream);
 int ctr_axpby(const float* a, float alpha, const float* b, float beta, int64_t n, float* out, ctr_stream_t stream);
 
+/* ---- K7/K8: all-pairs interactions (pair order i < j row-major; P = F(F-1)/2) -----------------------
+ * pnn_product: z[b] = [x[b] (F*K) | inner (P)]            (outer = 0; PNN.py:148-153)
+ *              z[b] = [x[b] (F*K) | outer (P*K*K)]        (outer = 1; PNN.py:164-167, "NOT ready yet")
+ *   bwd: dX = dz[:, :F*K] + product-rule terms of the tail.
+ * afm_pairs:  pw[b,p,:] = e_i * e_j (AFM.py:132-138);  bwd: dX[b,f,:] = sum_o dpw[b,pair(f,o),:] * e_o
+ * afm_pool:   att = softmax_p(logit) (AFM.py:151), w = dropout(att) (:152-153), y_emb = sum_p w_p pw_p (:156);
+ *   bwd: dpw = w * dy_emb (written), dlogit = softmax backward.
+ * dropout_apply: out = x / keep * mask  (NFM's dropout on the bi-interaction vector, NFM.py:136-137;
+ *   AFM's on y_emb, AFM.py:157-158) */
+int ctr_pnn_product_fwd(const float* x, int B, int F, int K, int outer, float* z, ctr_stream_t stream);
+int ctr_pnn_product_bwd(const float* x, const float* dz, int B, int F, int K, int outer, float* dX,
+                        ctr_stream_t stream);
+int ctr_afm_pairs_fwd(const float* x, int B, int F, int K, float* pw, ctr_stream_t stream);
+int ctr_afm_pairs_bwd(const float* x, const float* dpw, int B, int F, int K, float* dX, ctr_stream_t stream);
+int ctr_afm_pool_fwd(const float* pw, const float* logit, const float* mask, float keep, int B, int P, int K,
+                     float* att, float* y_emb, ctr_stream_t stream);
+int ctr_afm_pool_bwd(const float* pw, const float* att, const float* mask, float keep, const float* dy_emb, int B,
+                     int P, int K, float* dpw, float* dlogit, ctr_stream_t stream);
+int ctr_dropout_apply(const float* x, const float* mask, float keep, int64_t n, float* out, ctr_stream_t stream);
+
 /* ---- libsvm input (HOST buffers) -------------------------------------------------------------------
  * decode_libsvm of input_fn (DeepFM.py:65-81): "<label> <id>:<val> ..." lines -> ids int32 [rows,F],
  * vals f32 [rows,F], labels f32 [rows].  Parses complete lines of buf_host[0,len) up to max_rows;

@@ -75,6 +75,13 @@ SIGNATURES = {
     "ctr_din_pool_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P]),
     "ctr_group_sum": (c_int, [P, c_int, c_int, c_int, P, P]),
     "ctr_axpby": (c_int, [P, c_float, P, c_float, c_int64, P, P]),
+    "ctr_pnn_product_fwd": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
+    "ctr_pnn_product_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
+    "ctr_afm_pairs_fwd": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "ctr_afm_pairs_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P]),
+    "ctr_afm_pool_fwd": (c_int, [P, P, P, c_float, c_int, c_int, c_int, P, P, P]),
+    "ctr_afm_pool_bwd": (c_int, [P, P, P, c_float, P, c_int, c_int, c_int, P, P, P]),
+    "ctr_dropout_apply": (c_int, [P, P, c_float, c_int64, P, P]),
     "ctr_parse_libsvm": (c_int64, [c_char_p, c_size_t, c_int, c_int64, c_int, P, P, P, ctypes.POINTER(c_size_t)]),
     "ctr_libsvm_count_fields": (c_int, [c_char_p, c_size_t]),
     "ctr_init_trunc_normal": (c_int, [P, c_int64, c_float, c_uint64, P]),

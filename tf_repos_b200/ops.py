@@ -293,6 +293,43 @@ def axpby(a, alpha, b, beta, out):
                        _p(out, torch.float32, "out"), _stream()), "ctr_axpby")
 
 
+def pnn_product_fwd(x, B, F, K, outer, z):
+    check(_L.ctr_pnn_product_fwd(_p(x, torch.float32, "x"), B, F, K, int(outer), _p(z, torch.float32, "z"), _stream()),
+          "ctr_pnn_product_fwd")
+
+
+def pnn_product_bwd(x, dz, B, F, K, outer, dX):
+    check(_L.ctr_pnn_product_bwd(_p(x, torch.float32, "x"), _p(dz, torch.float32, "dz"), B, F, K, int(outer),
+                                 _p(dX, torch.float32, "dX"), _stream()), "ctr_pnn_product_bwd")
+
+
+def afm_pairs_fwd(x, B, F, K, pw):
+    check(_L.ctr_afm_pairs_fwd(_p(x, torch.float32, "x"), B, F, K, _p(pw, torch.float32, "pw"), _stream()),
+          "ctr_afm_pairs_fwd")
+
+
+def afm_pairs_bwd(x, dpw, B, F, K, dX):
+    check(_L.ctr_afm_pairs_bwd(_p(x, torch.float32, "x"), _p(dpw, torch.float32, "dpw"), B, F, K,
+                               _p(dX, torch.float32, "dX"), _stream()), "ctr_afm_pairs_bwd")
+
+
+def afm_pool_fwd(pw, logit, mask, keep, B, P, K, att, y_emb):
+    check(_L.ctr_afm_pool_fwd(_p(pw, torch.float32, "pw"), _p(logit, torch.float32, "logit"), _p(mask, torch.float32, "mask"),
+                              float(keep), B, P, K, _p(att, torch.float32, "att"), _p(y_emb, torch.float32, "y_emb"),
+                              _stream()), "ctr_afm_pool_fwd")
+
+
+def afm_pool_bwd(pw, att, mask, keep, dy_emb, B, P, K, dpw, dlogit):
+    check(_L.ctr_afm_pool_bwd(_p(pw, torch.float32, "pw"), _p(att, torch.float32, "att"), _p(mask, torch.float32, "mask"),
+                              float(keep), _p(dy_emb, torch.float32, "dy_emb"), B, P, K, _p(dpw, torch.float32, "dpw"),
+                              _p(dlogit, torch.float32, "dlogit"), _stream()), "ctr_afm_pool_bwd")
+
+
+def dropout_apply(x, mask, keep, out):
+    check(_L.ctr_dropout_apply(_p(x, torch.float32, "x"), _p(mask, torch.float32, "mask"), float(keep), x.numel(),
+                               _p(out, torch.float32, "out"), _stream()), "ctr_dropout_apply")
+
+
 def epoch_max_steps() -> int:
     return int(_L.ctr_epoch_max_steps())
 
