@@ -325,6 +325,133 @@ class DCN(OracleModel, MLPMixin):
         return {"y": y, "x0": x0, "xL": xl}
 
 
+class _LinearEmb(OracleModel, MLPMixin):
+    """Shared by NFM / PNN / AFM: variables `bias`, `linear`, `emb`; L2 on linear and emb."""
+
+    tables = ("linear", "emb")
+    l2_vars = ("linear", "emb")  # NFM.py:169, PNN.py:207, AFM.py:181
+
+    def _base(self, field_size, feature_size, embedding_size, gen):
+        self.F, self.N, self.K = field_size, feature_size, embedding_size
+        self.bn_state = {}
+        self.add_param("bias", torch.zeros(1))
+        self.add_param("linear", tfs.glorot_normal((self.N,), gen, self.dtype))
+        self.add_param("emb", tfs.glorot_normal((self.N, self.K), gen, self.dtype))
+
+    def sites(self, batch):
+        ids = batch["feat_ids"].reshape(-1, self.F)
+        return {"w": ("linear", ids), "v": ("emb", ids)}
+
+    def _lin_emb(self, rows, batch):
+        vals = batch["feat_vals"].reshape(-1, self.F).to(self.dtype)
+        y_linear = (rows["w"] * vals).sum(1)
+        emb = rows["v"] * vals.reshape(-1, self.F, 1)
+        return y_linear, emb
+
+
+class NFM(_LinearEmb):
+    """NFM.py:94-200."""
+
+    def __init__(self, field_size, feature_size, embedding_size, deep_layers="128,64", dropout="0.5,0.8,0.8", seed=0, **kw):
+        kw.setdefault("l2_reg", 0.001); kw.setdefault("learning_rate", 0.05)
+        super().__init__(**kw)
+        self.layers, self.keep = _ints(deep_layers), _floats(dropout)
+        gen = torch.Generator().manual_seed(seed)
+        self._base(field_size, feature_size, embedding_size, gen)
+        self.build_mlp(self.K, self.layers, gen)
+        self.init_slots()
+
+    def forward(self, rows, dense, batch, train, masks=None):
+        y_linear, emb = self._lin_emb(rows, batch)
+        x = 0.5 * (emb.sum(1) ** 2 - (emb ** 2).sum(1))                                   # NFM.py:126-128
+        if train:
+            x = tfs.dropout(x, self.keep[0], None if masks is None else masks.get("bi"))  # :136-137
+        h = self.run_mlp(x, dense, self.layers, self.keep, train, None if masks is None else masks.get("mlp"))
+        y_d = tfs.fully_connected(h, dense["Deep-part/deep_out/weights"], dense["Deep-part/deep_out/biases"], None).reshape(-1)
+        y = dense["bias"] * torch.ones_like(y_d) + y_linear + y_d                          # :152-155
+        return {"y": y}
+
+
+class PNN(_LinearEmb):
+    """PNN.py:102-238, model_type in {FNN, Inner, Outer}."""
+
+    def __init__(self, field_size, feature_size, embedding_size, model_type="Inner", deep_layers="256,128,64",
+                 dropout="0.5,0.5,0.5", seed=0, **kw):
+        super().__init__(**kw)
+        self.model_type = model_type
+        self.layers, self.keep = _ints(deep_layers), _floats(dropout)
+        gen = torch.Generator().manual_seed(seed)
+        self._base(field_size, feature_size, embedding_size, gen)
+        P = field_size * (field_size - 1) // 2
+        dz = field_size * embedding_size + {"FNN": 0, "Inner": P, "Outer": P * embedding_size ** 2}[model_type]
+        self.build_mlp(dz, self.layers, gen)
+        self.init_slots()
+
+    def forward(self, rows, dense, batch, train, masks=None):
+        y_linear, emb = self._lin_emb(rows, batch)
+        B, F, K = emb.shape
+        x = emb.reshape(B, F * K)
+        if self.model_type == "FNN":
+            z = x
+        else:
+            row, col = [], []
+            for i in range(F - 1):                                                         # PNN.py:144-147
+                for j in range(i + 1, F):
+                    row.append(i); col.append(j)
+            p, q = emb[:, row], emb[:, col]
+            if self.model_type == "Inner":
+                z = torch.cat([x, (p * q).sum(-1)], 1)                                     # :152-153
+            else:
+                z = torch.cat([x, torch.einsum("api,apj->apij", p, q).reshape(B, -1)], 1)  # :166-167
+        h = self.run_mlp(z, dense, self.layers, self.keep, train, None if masks is None else masks.get("mlp"))
+        y_d = tfs.fully_connected(h, dense["Deep-part/deep_out/weights"], dense["Deep-part/deep_out/biases"], None).reshape(-1)
+        return {"y": dense["bias"] * torch.ones_like(y_d) + y_linear + y_d}                # :190-193
+
+
+class AFM(_LinearEmb):
+    """AFM.py:99-212."""
+
+    ATT, POOL = "Attention-part", "Attention-based-Pooling"
+
+    def __init__(self, field_size, feature_size, embedding_size, attention_layers="256", dropout="1.0,0.5", seed=0, **kw):
+        kw.setdefault("l2_reg", 1.0); kw.setdefault("learning_rate", 0.1)
+        super().__init__(**kw)
+        self.att_layers, self.keep = _ints(attention_layers), _floats(dropout)
+        gen = torch.Generator().manual_seed(seed)
+        self._base(field_size, feature_size, embedding_size, gen)
+        d = self.K
+        for i, a in enumerate(self.att_layers):
+            self.add_param(f"{self.ATT}/mlp{i}/weights", tfs.xavier_uniform((d, a), gen, self.dtype))
+            self.add_param(f"{self.ATT}/mlp{i}/biases", torch.zeros(a, dtype=self.dtype))
+            d = a
+        self.add_param(f"{self.ATT}/attention_out/weights", tfs.xavier_uniform((d, 1), gen, self.dtype))
+        self.add_param(f"{self.ATT}/attention_out/biases", torch.zeros(1, dtype=self.dtype))
+        self.add_param(f"{self.POOL}/deep_out/weights", tfs.xavier_uniform((self.K, 1), gen, self.dtype))
+        self.add_param(f"{self.POOL}/deep_out/biases", torch.zeros(1, dtype=self.dtype))
+        self.init_slots()
+
+    def forward(self, rows, dense, batch, train, masks=None):
+        y_linear, emb = self._lin_emb(rows, batch)
+        B, F, K = emb.shape
+        prods = [emb[:, i, :] * emb[:, j, :] for i in range(F) for j in range(i + 1, F)]   # AFM.py:134-136
+        pw = torch.stack(prods).permute(1, 0, 2)                                           # :137-138
+        P = pw.shape[1]
+        h = pw.reshape(-1, K)
+        for i in range(len(self.att_layers)):
+            h = tfs.fully_connected(h, dense[f"{self.ATT}/mlp{i}/weights"], dense[f"{self.ATT}/mlp{i}/biases"], "relu")
+        aij = tfs.fully_connected(h, dense[f"{self.ATT}/attention_out/weights"], dense[f"{self.ATT}/attention_out/biases"], None)
+        soft = torch.softmax(aij.reshape(B, P, 1), dim=1)                                  # :151
+        if train:
+            soft = tfs.dropout(soft, self.keep[0], None if masks is None or masks.get("att") is None
+                               else masks["att"].reshape(B, P, 1))                         # :152-153
+        y_emb = (soft * pw).sum(1)                                                         # :156
+        if train:
+            y_emb = tfs.dropout(y_emb, self.keep[1], None if masks is None else masks.get("pool"))  # :157-158
+        y_deep = tfs.fully_connected(y_emb, dense[f"{self.POOL}/deep_out/weights"], dense[f"{self.POOL}/deep_out/biases"],
+                                     None).reshape(-1)
+        return {"y": dense["bias"] * torch.ones_like(y_deep) + y_linear + y_deep}          # :164-167
+
+
 class DIN(OracleModel, MLPMixin):
     """DIN.py:101-257.  batch keys: feat_ids [B,F'], a_ids [3,B], a_int_ids [nnz] + a_int_off [B+1],
     u_ids [4,B,P] / u_wgt [4,B,P] (0-padded, as sparse_tensor_to_dense produces, DIN.py:153-154)."""
