@@ -282,6 +282,16 @@ int ctr_afm_pool_bwd(const float* pw, const float* att, const float* mask, float
                      int P, int K, float* dpw, float* dlogit, ctr_stream_t stream);
 int ctr_dropout_apply(const float* x, const float* mask, float keep, int64_t n, float* out, ctr_stream_t stream);
 
+/* ---- row-sharded table routing (not in the reference) ---------------------------------
+ * owner(id) = id % G, local row = id / G.  bucket_ids: the *n_uniq sorted unique ids of a batch are
+ * grouped by owner: counts[G]; order[pos] = index into uniq; pos_of[u] = pos; local_ids[pos] = id / G
+ * (bucket-major: the send buffer of the id all-to-all).  remap_ids: out[i] = pos_of[inverse[i]] turns
+ * the batch's ids into indices of the received row cache.  gather_scalar: out[i] = W[ids[i]]. */
+int ctr_a2a_bucket_ids(const int32_t* uniq, const int32_t* n_uniq, int64_t n_max, int G, int32_t* counts,
+                       int32_t* cursor, int32_t* order, int32_t* pos_of, int32_t* local_ids, ctr_stream_t stream);
+int ctr_remap_ids(const int32_t* inverse, const int32_t* pos_of, int64_t n, int32_t* out, ctr_stream_t stream);
+int ctr_gather_scalar(const int32_t* ids, const float* W, int64_t N, int64_t n, float* out, ctr_stream_t stream);
+
 /* ---- libsvm input (HOST buffers) -------------------------------------------------------------------
  * decode_libsvm of input_fn (DeepFM.py:65-81): "<label> <id>:<val> ..." lines -> ids int32 [rows,F],
  * vals f32 [rows,F], labels f32 [rows].  Parses complete lines of buf_host[0,len) up to max_rows;

@@ -82,6 +82,9 @@ SIGNATURES = {
     "ctr_afm_pool_fwd": (c_int, [P, P, P, c_float, c_int, c_int, c_int, P, P, P]),
     "ctr_afm_pool_bwd": (c_int, [P, P, P, c_float, P, c_int, c_int, c_int, P, P, P]),
     "ctr_dropout_apply": (c_int, [P, P, c_float, c_int64, P, P]),
+    "ctr_a2a_bucket_ids": (c_int, [P, P, c_int64, c_int, P, P, P, P, P, P]),
+    "ctr_remap_ids": (c_int, [P, P, c_int64, P, P]),
+    "ctr_gather_scalar": (c_int, [P, P, c_int64, c_int64, P, P]),
     "ctr_parse_libsvm": (c_int64, [c_char_p, c_size_t, c_int, c_int64, c_int, P, P, P, ctypes.POINTER(c_size_t)]),
     "ctr_libsvm_count_fields": (c_int, [c_char_p, c_size_t]),
     "ctr_init_trunc_normal": (c_int, [P, c_int64, c_float, c_uint64, P]),

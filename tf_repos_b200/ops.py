@@ -330,6 +330,22 @@ def dropout_apply(x, mask, keep, out):
                                _p(out, torch.float32, "out"), _stream()), "ctr_dropout_apply")
 
 
+def a2a_bucket_ids(uniq, n_uniq, n_max, G, counts, cursor, order, pos_of, local_ids):
+    check(_L.ctr_a2a_bucket_ids(_p(uniq, torch.int32), _p(n_uniq, torch.int32), n_max, G, _p(counts, torch.int32),
+                                _p(cursor, torch.int32), _p(order, torch.int32), _p(pos_of, torch.int32),
+                                _p(local_ids, torch.int32), _stream()), "ctr_a2a_bucket_ids")
+
+
+def remap_ids(inverse, pos_of, n, out):
+    check(_L.ctr_remap_ids(_p(inverse, torch.int32), _p(pos_of, torch.int32), n, _p(out, torch.int32), _stream()),
+          "ctr_remap_ids")
+
+
+def gather_scalar(ids, W, out):
+    check(_L.ctr_gather_scalar(_p(ids, torch.int32, "ids"), _p(W, torch.float32, "W"), W.numel(), ids.numel(),
+                               _p(out, torch.float32, "out"), _stream()), "ctr_gather_scalar")
+
+
 def epoch_max_steps() -> int:
     return int(_L.ctr_epoch_max_steps())
 
