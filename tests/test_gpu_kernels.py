@@ -384,11 +384,17 @@ def test_fc_fwd_bwd(M, Kd, Nd, drop):
     mask = (torch.rand(M, Nd, generator=g) < keep).float() if drop else None
     dOut = torch.randn(M, Nd, generator=g)
     xd, Wd, bd = x.double().requires_grad_(), W.double().requires_grad_(), b.double().requires_grad_()
-    z = torch.relu(xd @ Wd + bd)
-    out_ref = z / keep * mask.double() if drop else z
-    out_ref.backward(dOut.double())
     out = torch.empty(M, Nd, device=d)
     ops.fc_fwd(x.to(d), W.to(d), b.to(d), mask.to(d) if drop else None, keep, 1, out)
+    pre = xd @ Wd + bd
+    # a pre-activation within rounding distance of 0 may land on either side of the relu: the reference
+    # takes the GPU's side for those (otherwise one flipped unit perturbs a whole row of dIn)
+    act = (out.cpu() > 0).double() if not drop else ((out.cpu() > 0) | (mask == 0) & (pre.detach() > 0)).double()
+    near = pre.detach().abs() < 1e-4
+    gate = torch.where(near, act, (pre.detach() > 0).double())
+    z = pre * gate
+    out_ref = z / keep * mask.double() if drop else z
+    out_ref.backward(dOut.double())
     _close(out, out_ref, rtol=2e-6 * Kd ** 0.5, what="fc out")
     dO = dOut.to(d).clone()
     dIn = torch.empty(M, Kd, device=d); dW = torch.empty(Kd, Nd, device=d); db = torch.empty(Nd, device=d)

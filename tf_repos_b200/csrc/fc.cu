@@ -10,6 +10,9 @@
 //   backward  dIn[M,K]  = dZ[M,N] @ W[K,N]^T                 (A reduce-contiguous, B reduce-contiguous)
 //             dW[K,N]   = in[M,K]^T @ dZ[M,N]  (split over M, deterministic two-pass reduction)
 // Accumulation order over the reduction dimension is fixed => bit-reproducible run to run.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace ctr {
@@ -225,9 +228,24 @@ __global__ void dropout_mask_kernel(float* __restrict__ mask, int64_t n, float k
   }
 }
 
+// tc_gemm.cu: the same products on tcgen05 tensor cores (3xTF32).  CTR_GEMM=simt selects the SIMT tiles.
+int tc_gemm_dispatch(int kind, int epi, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N,
+                     int R, int S, const float* bias, int act, const float* mask, float keep, const float* gbias, int gP,
+                     cudaStream_t st);
+
+static bool use_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CTR_GEMM");
+    v = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int pick_split(int M, int N, int R) {
   // dW-style product: few output tiles, long reduction => split R so that >= ~2 waves of CTAs exist
-  const int tiles = ((M + 63) / 64) * ((N + 63) / 64);
+  const int t = use_tc() ? 128 : 64;
+  const int tiles = ((M + t - 1) / t) * ((N + t - 1) / t);
   int s = (2 * sm_count() + tiles - 1) / tiles;
   if (s < 1) s = 1;
   const int max_s = (R + 255) / 256;
@@ -260,7 +278,9 @@ int ctr_fc_fwd_grouped(const float* in, const float* Wt, const float* b, const f
   CTR_REQUIRE(in && Wt && out, CTR_ERR_INVALID_ARG, "ctr_fc_fwd: null buffer");
   CTR_REQUIRE(!drop_mask || keep_prob > 0.f, CTR_ERR_INVALID_ARG, "ctr_fc_fwd: keep_prob must be > 0");
   cudaStream_t st = as_stream(stream);
-  if (Nd >= 128) {
+  if (use_tc()) {
+    tc_gemm_dispatch(0, 1, in, Kd, Wt, Nd, out, Nd, M, Nd, Kd, 1, b, act, drop_mask, keep_prob, group_bias, group_P, st);
+  } else if (Nd >= 128) {
     dim3 grid((Nd + 127) / 128, (M + 63) / 64, 1);
     gemm_tile_kernel<64, 128, 4, 8, true, false, 1><<<grid, 256, 0, st>>>(in, Kd, Wt, Nd, out, Nd, M, Nd, Kd, b, act,
                                                                           drop_mask, keep_prob, group_bias, group_P);
@@ -300,9 +320,13 @@ int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* 
   // 2. dW[Kd,Nd] = in^T @ dZ, split over M
   const int S = pick_split(Kd, Nd, M);
   {
-    dim3 grid((Nd + 63) / 64, (Kd + 63) / 64, S);
-    gemm_tile_kernel<64, 64, 4, 4, false, false, 0><<<grid, 256, 0, st>>>(in, Kd, dOut, Nd, S == 1 ? dW : dw_part, Nd,
-                                                                          Kd, Nd, M, nullptr, 0, nullptr, 1.f, nullptr, 1);
+    if (use_tc()) {
+      tc_gemm_dispatch(2, 0, in, Kd, dOut, Nd, S == 1 ? dW : dw_part, Nd, Kd, Nd, M, S, nullptr, 0, nullptr, 1.f, nullptr, 1, st);
+    } else {
+      dim3 grid((Nd + 63) / 64, (Kd + 63) / 64, S);
+      gemm_tile_kernel<64, 64, 4, 4, false, false, 0><<<grid, 256, 0, st>>>(in, Kd, dOut, Nd, S == 1 ? dW : dw_part, Nd,
+                                                                            Kd, Nd, M, nullptr, 0, nullptr, 1.f, nullptr, 1);
+    }
     CTR_LAUNCHED("fc_dw");
     if (S > 1) {
       const int64_t n = (int64_t)Kd * Nd;
@@ -311,7 +335,10 @@ int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* 
     }
   }
   // 3. dIn[M,Kd] = dZ @ W^T
-  if (dIn) {
+  if (dIn && use_tc()) {
+    tc_gemm_dispatch(1, accumulate_din ? 2 : 0, dOut, Nd, Wt, Nd, dIn, Kd, M, Kd, Nd, 1, nullptr, 0, nullptr, 1.f, nullptr, 1, st);
+    CTR_LAUNCHED("fc_din");
+  } else if (dIn) {
     dim3 grid((Kd + 127) / 128, (M + 63) / 64, 1);
     if (accumulate_din)
       gemm_tile_kernel<64, 128, 4, 8, true, true, 2><<<grid, 256, 0, st>>>(dOut, Nd, Wt, Nd, dIn, Kd, M, Kd, Nd, nullptr,
