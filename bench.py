@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=CFG["batch_size"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the lazy/infer side measurements")
+    ap.add_argument("--tables", default="auto", choices=["auto", "replicated", "sharded"],
+                    help="N>1: 'sharded' = rows owned by id %% N, NCCL all-to-all exchange (default); "
+                         "'replicated' = data parallel with all-gathered sparse gradients")
     return ap.parse_args()
 
 
@@ -163,7 +166,8 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sps, ms, done, cores, desc = run_cpu(args.steps, args.warmup, 240.0, args.vocab, args.batch)
+    # one warm-up step and a wall-clock budget: a full-vocabulary CPU step takes seconds to tens of seconds
+    sps, ms, done, cores, desc = run_cpu(args.steps, min(args.warmup, 1), 150.0, args.vocab, args.batch)
     line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -199,9 +203,18 @@ def main_b200(args):
     c = CFG
     N, B, F, K = args.vocab, args.batch, c["field_size"], c["embedding_size"]
 
-    model = DeepFM(F, N, K, B, deep_layers=c["deep_layers"], dropout=c["dropout"], l2_reg=c["l2_reg"],
-                   learning_rate=c["learning_rate"], optimizer=c["optimizer"], update_mode="exact_deferred",
-                   epoch_steps=EPOCH, device=dev, seed=0, world=world)
+    sharded = world > 1 and args.tables in ("auto", "sharded")
+    if sharded:
+        # every rank owns the rows id % world == rank (and sweeps only those); ids / rows / gradient rows
+        # travel by NCCL all-to-all.  Same result as one GPU on the concatenated batch (tests/test_gpu_sharded.py).
+        from tf_repos_b200.sharded import ShardedDeepFM
+        model = ShardedDeepFM(F, N, K, B, deep_layers=c["deep_layers"], dropout=c["dropout"], l2_reg=c["l2_reg"],
+                              learning_rate=c["learning_rate"], optimizer=c["optimizer"],
+                              update_mode="exact_deferred", epoch_steps=EPOCH, device=dev, seed=0)
+    else:
+        model = DeepFM(F, N, K, B, deep_layers=c["deep_layers"], dropout=c["dropout"], l2_reg=c["l2_reg"],
+                       learning_rate=c["learning_rate"], optimizer=c["optimizer"], update_mode="exact_deferred",
+                       epoch_steps=EPOCH, device=dev, seed=0, world=world)
     host = [synth.criteo_batch(B, N, F, seed=rank * 1000 + i) for i in range(N_BATCHES)]
     devb = [tuple(t.to(dev) for t in b) for b in host]
     pinned = [tuple(t.pin_memory() for t in b) for b in host]
@@ -267,7 +280,7 @@ def main_b200(args):
         ids_d.copy_(hi, non_blocking=True); vals_d.copy_(hv, non_blocking=True); lab_d.copy_(hl, non_blocking=True)
         parts = model.train_step(ids_d, vals_d, lab_d)
         loss_h[i % loss_h.shape[0]].copy_(parts, non_blocking=True)       # CE of this step
-        if model.epoch_pos == 0:                                          # L2 terms of the epoch just closed
+        if model.epoch_pos == 0 and not sharded:                          # L2 terms of the epoch just closed
             reg_h.copy_(model.epoch_reg_terms(), non_blocking=True)
 
     ms_e2e = timed(step_host, args.steps, 2, finish=model.flush)
@@ -277,7 +290,7 @@ def main_b200(args):
 
     extras = {}
     exact_sweep_ms = []
-    if not args.no_extras:
+    if not args.no_extras and not sharded:
         model.set_update_mode("exact")
         model.updater.sweep_events = []
         ms_ex = timed(step_dev, max(args.steps // 2, 4), 2)
@@ -304,7 +317,8 @@ def main_b200(args):
         return
 
     peak, peak_src = peaks()
-    table_bytes = N * K * 4 * 6  # Adam: read var,m,v + write var,m,v (24 B/element) per pass over the table
+    n_rows = model.N_local if sharded else N
+    table_bytes = n_rows * K * 4 * 6  # Adam: read var,m,v + write var,m,v (24 B/element) per pass over the table
     sweep_avg_ms = sum(sweep_ms) / max(len(sweep_ms), 1)
     achieved = table_bytes / (sweep_avg_ms * 1e-3) / 1e9 if sweep_ms else None
     traffic = None
@@ -323,8 +337,11 @@ def main_b200(args):
                                    "every step); the timed region ends with a flush of all deferred work",
                        "vocab": N, "batch_per_gpu": B, "l2_flush": "inputs larger than L2: every epoch streams the "
                        "whole 38.4 GB fm_v/m/v state; 16 distinct pre-staged batches are cycled",
-                       "parallelism": ("single GPU" if world == 1 else f"dp{world}: replicated tables, all-gather of "
-                                       "sparse gradients, all-reduce of dense gradients")},
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"dp{world} batches, tables row-sharded by id % {world}: NCCL all-to-all of ids / "
+                                       "rows / gradient rows, all-reduce of dense gradients" if sharded else
+                                       f"dp{world}: replicated tables, all-gather of sparse gradients, all-reduce of "
+                                       "dense gradients")},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12 + 8, "last_loss": last_loss},
             "gpu_launches": launches, "clocks": sampler.summary(),

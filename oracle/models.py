@@ -170,7 +170,11 @@ class OracleModel:
             # TensorFlow: the dense l2 gradient is converted to IndexedSlices over ALL rows and
             # concatenated with the gather gradients => every row is an index of the sparse apply.
             if regularised:
-                G = l2 * var
+                if var.numel() >= (1 << 24):
+                    G = tfs._scratch(var, 2)
+                    torch.mul(var, l2, out=G)
+                else:
+                    G = l2 * var
                 G[uniq] = summed + G[uniq]
                 self._apply_rows(var, slots, G, sparse=True)
             elif self.optimizer == "Adam":

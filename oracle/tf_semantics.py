@@ -220,12 +220,38 @@ class AdamHyper:
         self.b2p = self.b2p * self.b2
 
 
+_SCRATCH = {}
+
+
+def _scratch(like: torch.Tensor, slot: int) -> torch.Tensor:
+    key = (tuple(like.shape), like.dtype, slot)
+    if key not in _SCRATCH:
+        _SCRATCH.clear() if len(_SCRATCH) > 8 else None
+        _SCRATCH[key] = torch.empty_like(like)
+    return _SCRATCH[key]
+
+
 def adam_sparse_(var, m, v, g, lr_t, b1, b2, eps):
     """AdamOptimizer._apply_sparse_shared [TF-sem] on the rows given (in place):
         m <- m*b1 ; m += g*(1-b1) ; v <- v*b2 ; v += (g*g)*(1-b2)
         var <- var - (lr_t*m)/(sqrt(v)+eps)
-    (TF decays m and v of EVERY row and updates every row of var; callers pass whole tables.)"""
+    (TF decays m and v of EVERY row and updates every row of var; callers pass whole tables.)
+    Large tables take the same op-by-op arithmetic through two reused scratch buffers (the timed CPU
+    baseline would otherwise spend most of its time page-faulting fresh 12.8 GB temporaries, which TF's
+    BFC allocator does not do)."""
     one = torch.ones((), dtype=var.dtype)
+    if var.numel() >= (1 << 24) and g.shape == var.shape:
+        t = _scratch(var, 0)
+        torch.mul(g, one - b1, out=t); m.mul_(b1); m.add_(t)
+        torch.mul(g, g, out=t); t.mul_(one - b2); v.mul_(b2); v.add_(t)
+        torch.mul(m, lr_t, out=t)
+        d = _scratch(var, 1)
+        if FAST_SQRT or var.dtype != F32:
+            torch.sqrt(v, out=d)
+        else:
+            d.copy_(ieee_sqrt(v))
+        d.add_(eps); t.div_(d); var.sub_(t)
+        return
     m.mul_(b1).add_(g * (one - b1))
     v.mul_(b2).add_((g * g) * (one - b2))
     var.sub_((lr_t * m) / (ieee_sqrt(v) + eps))

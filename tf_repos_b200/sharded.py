@@ -11,7 +11,7 @@ owner(id) = id % G, local row = id // G.  One process per GPU, data-parallel bat
             on the local shard (exact sweep / exact_deferred epochs / lazy); dense grads: all_reduce.
 
 The result equals the single-GPU engine on the concatenated batch.  The collectives are NCCL
-(torch.distributed) on the compute stream; split sizes are exchanged first (two small host syncs/step).
+(torch.distributed) on the compute stream; the bucket sizes of all ranks are all-gathered first (one small host sync per step).
 """
 from __future__ import annotations
 
@@ -68,6 +68,7 @@ class ShardedDeepFM:
         self.uw = ops.UniqueWorkspace(n, self.N, dev)            # unique of my batch's global ids
         self.uw2 = ops.UniqueWorkspace(n, n, dev)                # segment structure over cache positions
         self.counts = torch.zeros(G, **i32); self.cursor = torch.zeros(G, **i32)
+        self.count_mat = torch.zeros(G * G, **i32)
         self.order = torch.empty(n, **i32); self.pos_of = torch.empty(n, **i32)
         self.local_ids = torch.empty(n, **i32); self.ids_remap = torch.empty(n, **i32)
         self.cache_v = torch.empty(n, K, **f32); self.cache_w = torch.empty(n, **f32)
@@ -123,15 +124,15 @@ class ShardedDeepFM:
         ops.a2a_bucket_ids(self.uw.uniq, self.uw.n_uniq, n, G, self.counts, self.cursor, self.order, self.pos_of,
                            self.local_ids)
         ops.remap_ids(self.uw.inverse, self.pos_of, n, self.ids_remap[:n])
-        send = self.counts.tolist()                                    # host sync #1
-        U = sum(send)
-        if G > 1:
-            rc = torch.empty_like(self.counts)
-            dist.all_to_all_single(rc, self.counts, group=self.group)
-            recv = rc.tolist()                                         # host sync #2
+        if G > 1:   # every rank's bucket sizes in one collective, one host sync per step
+            dist.all_gather_into_tensor(self.count_mat, self.counts, group=self.group)
+            cm = self.count_mat.view(G, G).tolist()
+            send = cm[self.rank]
+            recv = [cm[r][self.rank] for r in range(G)]
         else:
+            send = self.counts.tolist()
             recv = list(send)
-        R = sum(recv)
+        U, R = sum(send), sum(recv)
         self._a2a(self.recv_ids[:R], self.local_ids[:U], recv, send)
         if deferred_j is not None:   # owners bring the requested rows to the start of this step
             self.updater.unique(self.recv_ids[:R])
