@@ -182,6 +182,11 @@ int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* la
 /* reg[s] (+)= scale*(ss_rows[s] + sum_b ss_partials[s][b]) for s < upto; clears ss_rows[s] */
 int ctr_epoch_reg_loss(double* ss_rows, const double* ss_partials, int n_partials, int upto, float scale,
                        float* reg, int accumulate, ctr_stream_t stream);
+/* Diagnostics: the epoch sweeps evaluate sqrt/div through hand-scheduled IEEE fast paths with one range
+ * check per four elements (optim_steps.cuh).  This compares them, bit for bit, with the compiler's
+ * sqrt.rn / div.rn on n pseudo-random in-range operands (seeded; uniform mantissas, hard mantissa
+ * patterns mixed in).  mismatches: device int64[2] = {sqrt mismatches, div mismatches} (overwritten). */
+int ctr_selftest_divsqrt(uint64_t seed, int64_t n, int64_t* mismatches, ctr_stream_t stream);
 
 /* ---- loss head -----------------------------------------------------------------------------------
  * y = ((bias + y_a) + y_b) + y_c (NULL terms skipped; DeepFM.py:172-175), pred = sigmoid(y)

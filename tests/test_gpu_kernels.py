@@ -447,3 +447,13 @@ def test_dropout_mask_rate_and_step_dependence():
     step.fill_(4.0)
     ops.dropout_mask(m2, 0.8, 7, step)
     assert not torch.equal(m, m2)
+
+
+@pytest.mark.gpu
+def test_inrange_sqrt_div_fast_paths_are_correctly_rounded():
+    """The epoch sweeps' grouped IEEE sqrt/div fast paths (optim_steps.cuh) vs the compiler's sqrt.rn/div.rn:
+    bit-identical on 2^31 seeded operands (random + hard mantissa patterns over the whole guarded range)."""
+    from tf_repos_b200 import ops
+    for seed in (1, 12345):
+        bad_sqrt, bad_div = ops.selftest_divsqrt(seed, 1 << 30, torch.device("cuda"))
+        assert (bad_sqrt, bad_div) == (0, 0)

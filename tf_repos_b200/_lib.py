@@ -52,6 +52,7 @@ SIGNATURES = {
     "ctr_epoch_sweep": (c_int, [c_int, P, P, P, P, c_int64, c_int, P, P, c_int, c_int, P,
                                 ctypes.POINTER(c_int), P]),
     "ctr_epoch_reg_loss": (c_int, [P, P, c_int, c_int, c_float, P, c_int, P]),
+    "ctr_selftest_divsqrt": (c_int, [c_uint64, c_int64, P, P]),
     "ctr_reduce_sum": (c_int, [P, c_int64, c_float, P, P, c_size_t, P]),
     "ctr_l2_loss_workspace_bytes": (c_size_t, [c_int64]),
     "ctr_l2_loss": (c_int, [P, c_int64, c_float, P, P, c_size_t, P]),

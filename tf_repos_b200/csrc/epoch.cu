@@ -142,6 +142,20 @@ epoch_rows_generic_kernel(float* __restrict__ var, float* __restrict__ slot0, fl
 // All rows: replay steps last[row]..upto-1, reset `last` where it was non-zero (reset == true) or
 // raise it to `upto` (mid-epoch flush).  ss_partials[s][block] = sum(var^2) of the state step s
 // started from, over this block's elements.
+// warp w reduces the per-thread accumulators of steps w, w+8, ... (fixed order => deterministic)
+__device__ __forceinline__ void sweep_ss_flush(float (*ss_thr)[256], int upto, double* __restrict__ ss_partials,
+                                               int n_partials) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int s = warp; s < upto; s += 8) {
+    double q = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q += (double)ss_thr[s][lane + 32 * k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(FULL_MASK, q, o);
+    if (lane == 0) ss_partials[(int64_t)s * n_partials + blockIdx.x] = q;
+  }
+}
+
 template <int OPT, int UNROLL, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 epoch_sweep_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
@@ -150,13 +164,14 @@ epoch_sweep_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __
                    double* __restrict__ ss_partials, int n_partials) {
   constexpr bool two = OptTraits<OPT>::slots == 2;
   __shared__ float lr_s[EPOCH_MAX];
-  __shared__ double ss_blk[EPOCH_MAX];
-  if (threadIdx.x < EPOCH_MAX) {
-    lr_s[threadIdx.x] = (threadIdx.x < upto) ? lr_table[threadIdx.x] : 0.f;
-    ss_blk[threadIdx.x] = 0.0;
-  }
+  // sum(var^2) seen at step s: one fp32 accumulator per thread and step (each takes a few thousand terms of
+  // similar size), reduced once at the end; the cross-CTA sum is double (ctr_epoch_reg_loss)
+  __shared__ float ss_thr[EPOCH_MAX][256];
+  if (threadIdx.x < EPOCH_MAX) lr_s[threadIdx.x] = (threadIdx.x < upto) ? lr_table[threadIdx.x] : 0.f;
+  for (int s = 0; s < upto; ++s) ss_thr[s][threadIdx.x] = 0.f;
   __syncthreads();
   Hyper h = load_hyper(hyper);
+  const AdamConsts ac = adam_consts(h);
   float4* v4 = reinterpret_cast<float4*>(var);
   float4* a4 = reinterpret_cast<float4*>(slot0);
   float4* b4 = reinterpret_cast<float4*>(slot1);
@@ -180,23 +195,39 @@ epoch_sweep_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __
         b[u] = two ? ld_stream4(b4 + i) : f4_zero();
         l0[u] = last[row_of(i)];
       } else {
+        x[u] = a[u] = b[u] = f4_zero();
         l0[u] = upto;
       }
     }
-    // common case: every lane replays steps 0..upto-1 (rows not gathered this epoch)
+    int lmax = l0[0];
+#pragma unroll
+    for (int u = 1; u < UNROLL; ++u) lmax = max(lmax, l0[u]);
+    const int wmax = __reduce_max_sync(FULL_MASK, lmax);   // from step wmax on, the whole warp advances
 #pragma unroll 1
     for (int s = 0; s < upto; ++s) {
       h.lr = lr_s[s];
       float q = 0.f;
+      if (OPT == CTR_OPT_ADAM) {
+        if (s >= wmax) {      // common case (rows not gathered this epoch): no masks
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        if (s >= l0[u]) {
-          q += sq4(x[u]);
-          step_untouched4<OPT>(x[u], a[u], b[u], h);
+          for (int u = 0; u < UNROLL; ++u) q += sq4(x[u]);
+          adam_untouched<UNROLL>(x, a, b, h, ac);
+        } else {              // some rows of this warp are already past step s
+          bool act[UNROLL];
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) { act[u] = s >= l0[u]; q += act[u] ? sq4(x[u]) : 0.f; }
+          adam_untouched<UNROLL, true>(x, a, b, h, ac, act);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          if (s >= l0[u]) {
+            q += sq4(x[u]);
+            step_untouched4<OPT>(x[u], a[u], b[u], h);
+          }
         }
       }
-      q = warp_sum(q);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&ss_blk[s], (double)q);
+      ss_thr[s][threadIdx.x] += q;
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -213,7 +244,7 @@ epoch_sweep_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __
     }
   }
   __syncthreads();
-  if (threadIdx.x < upto) ss_partials[(int64_t)threadIdx.x * n_partials + blockIdx.x] = ss_blk[threadIdx.x];
+  sweep_ss_flush(ss_thr, upto, ss_partials, n_partials);
 }
 
 // K == 1 (first-order weights fm_w): a float4 spans 4 rows, each with its own `last` byte
@@ -225,13 +256,14 @@ epoch_sweep_k1_kernel(float* __restrict__ var, float* __restrict__ slot0, float*
                       double* __restrict__ ss_partials, int n_partials) {
   constexpr bool two = OptTraits<OPT>::slots == 2;
   __shared__ float lr_s[EPOCH_MAX];
-  __shared__ double ss_blk[EPOCH_MAX];
-  if (threadIdx.x < EPOCH_MAX) {
-    lr_s[threadIdx.x] = (threadIdx.x < upto) ? lr_table[threadIdx.x] : 0.f;
-    ss_blk[threadIdx.x] = 0.0;
-  }
+  // sum(var^2) seen at step s: one fp32 accumulator per thread and step (each takes a few thousand terms of
+  // similar size), reduced once at the end; the cross-CTA sum is double (ctr_epoch_reg_loss)
+  __shared__ float ss_thr[EPOCH_MAX][256];
+  if (threadIdx.x < EPOCH_MAX) lr_s[threadIdx.x] = (threadIdx.x < upto) ? lr_table[threadIdx.x] : 0.f;
+  for (int s = 0; s < upto; ++s) ss_thr[s][threadIdx.x] = 0.f;
   __syncthreads();
   Hyper h = load_hyper(hyper);
+  const AdamConsts ac = adam_consts(h);
   float4* v4 = reinterpret_cast<float4*>(var);
   float4* a4 = reinterpret_cast<float4*>(slot0);
   float4* b4 = reinterpret_cast<float4*>(slot1);
@@ -248,16 +280,29 @@ epoch_sweep_k1_kernel(float* __restrict__ var, float* __restrict__ slot0, float*
     }
     const int l0 = ok ? (int)(lw & 255u) : upto, l1 = ok ? (int)((lw >> 8) & 255u) : upto;
     const int l2_ = ok ? (int)((lw >> 16) & 255u) : upto, l3 = ok ? (int)(lw >> 24) : upto;
+    const int wmax = __reduce_max_sync(FULL_MASK, max(max(l0, l1), max(l2_, l3)));
 #pragma unroll 1
     for (int s = 0; s < upto; ++s) {
       h.lr = lr_s[s];
       float q = 0.f;
+      if (OPT == CTR_OPT_ADAM) {   // all 4 rows in one block; rows already past step s are restored by selects
+        const float4 xo = x, ao = a, bo = b;
+        adam_untouched4(x, a, b, h, ac);
+        if (s >= wmax) {
+          q = sq4(xo);
+        } else {
+          if (s >= l0) q += xo.x * xo.x; else { x.x = xo.x; a.x = ao.x; b.x = bo.x; }
+          if (s >= l1) q += xo.y * xo.y; else { x.y = xo.y; a.y = ao.y; b.y = bo.y; }
+          if (s >= l2_) q += xo.z * xo.z; else { x.z = xo.z; a.z = ao.z; b.z = bo.z; }
+          if (s >= l3) q += xo.w * xo.w; else { x.w = xo.w; a.w = ao.w; b.w = bo.w; }
+        }
+      } else {
       if (s >= l0) { q += x.x * x.x; step_sparse<OPT>(x.x, a.x, b.x, __fmul_rn(h.l2, x.x), h); }
       if (s >= l1) { q += x.y * x.y; step_sparse<OPT>(x.y, a.y, b.y, __fmul_rn(h.l2, x.y), h); }
       if (s >= l2_) { q += x.z * x.z; step_sparse<OPT>(x.z, a.z, b.z, __fmul_rn(h.l2, x.z), h); }
       if (s >= l3) { q += x.w * x.w; step_sparse<OPT>(x.w, a.w, b.w, __fmul_rn(h.l2, x.w), h); }
-      q = warp_sum(q);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&ss_blk[s], (double)q);
+      }
+      ss_thr[s][threadIdx.x] += q;
     }
     if (ok) {
       if (min(min(l0, l1), min(l2_, l3)) < upto) {
@@ -273,7 +318,7 @@ epoch_sweep_k1_kernel(float* __restrict__ var, float* __restrict__ slot0, float*
     }
   }
   __syncthreads();
-  if (threadIdx.x < upto) ss_partials[(int64_t)threadIdx.x * n_partials + blockIdx.x] = ss_blk[threadIdx.x];
+  sweep_ss_flush(ss_thr, upto, ss_partials, n_partials);
 }
 
 // scalar table / K % 4 != 0: one thread per element
@@ -370,7 +415,58 @@ __global__ void epoch_reg_kernel(double* __restrict__ ss_rows, const double* __r
 
 using namespace ctr;
 
+// ---- self-test of the in-range IEEE sqrt / div fast paths (optim_steps.cuh) ------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// a float with exponent uniformly in [e_lo, e_hi] (unbiased) and a mantissa that is random or one of the
+// patterns that stress a divider / square root (all ones, all zeros, one bit, just below/above a power of 4)
+__device__ __forceinline__ float test_float(uint64_t r, int e_lo, int e_hi) {
+  const int e = e_lo + (int)((r >> 40) % (uint64_t)(e_hi - e_lo + 1));
+  uint32_t man = (uint32_t)r & 0x7FFFFFu;
+  switch ((r >> 32) & 15u) {
+    case 0: man = 0x7FFFFFu; break;
+    case 1: man = 0u; break;
+    case 2: man = 1u; break;
+    case 3: man = 0x7FFFFEu; break;
+    case 4: man = 1u << ((r >> 36) % 23); break;
+    case 5: man = 0x7FFFFFu ^ (1u << ((r >> 36) % 23)); break;
+    default: break;
+  }
+  return __uint_as_float(((uint32_t)(e + 127) << 23) | man);
+}
+__global__ void __launch_bounds__(256) selftest_divsqrt_kernel(uint64_t seed, int64_t n, unsigned long long* mism) {
+  unsigned long long bad_s = 0, bad_d = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t r0 = mix64(seed + 3 * (uint64_t)i), r1 = mix64(seed + 3 * (uint64_t)i + 1), r2 = mix64(seed + 3 * (uint64_t)i + 2);
+    const float v = test_float(r0, -101, 99);
+    if (__float_as_uint(sqrt_rn_inrange(v)) != __float_as_uint(__fsqrt_rn(v))) ++bad_s;
+    float a = test_float(r1, -60, 59), b = test_float(r2, -60, 59);
+    if (r1 >> 63) a = -a;
+    if ((r2 >> 62) & 1) b = __fadd_rn(__fsqrt_rn(v < 1e30f ? v : 1.f), 1e-8f);   // the Adam denominator shape
+    if (fabsf(b) < DIV_LO || fabsf(b) > DIV_HI) b = 1.f;
+    if (__float_as_uint(div_rn_inrange(a, b)) != __float_as_uint(__fdiv_rn(a, b))) ++bad_d;
+  }
+  if (bad_s) atomicAdd(&mism[0], bad_s);
+  if (bad_d) atomicAdd(&mism[1], bad_d);
+}
+
 extern "C" {
+
+int ctr_selftest_divsqrt(uint64_t seed, int64_t n, int64_t* mismatches, ctr_stream_t stream) {
+  CTR_REQUIRE(mismatches && n >= 0, CTR_ERR_INVALID_ARG, "ctr_selftest_divsqrt: bad args");
+  cudaStream_t st = as_stream(stream);
+  CTR_REQUIRE(cudaMemsetAsync(mismatches, 0, 2 * sizeof(int64_t), st) == cudaSuccess, CTR_ERR_CUDA,
+              "ctr_selftest_divsqrt: memset failed");
+  if (n == 0) return CTR_OK;
+  selftest_divsqrt_kernel<<<sm_count() * 8, 256, 0, st>>>(seed, n, reinterpret_cast<unsigned long long*>(mismatches));
+  CTR_LAUNCHED("ctr_selftest_divsqrt");
+  return CTR_OK;
+}
+
 
 int ctr_epoch_max_steps(void) { return EPOCH_MAX; }
 
@@ -429,10 +525,10 @@ int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* la
   static int cfg = -1;
   if (cfg < 0) {
     const char* e = getenv("CTR_EPOCH_CFG");
-    cfg = e ? atoi(e) : 1;  // (unroll 2, 4 CTAs/SM) measured fastest on B200: profiles/
-    if (cfg < 0 || cfg > 3) cfg = 1;
+    cfg = e ? atoi(e) : 4;  // (unroll 2, 3 CTAs/SM) measured fastest on B200 with ~1.6 % gathered rows: profiles/
+    if (cfg < 0 || cfg > 7) cfg = 4;
   }
-  static const int kBlocksPerSm[4] = {3, 4, 2, 6};
+  static const int kBlocksPerSm[8] = {3, 4, 2, 6, 3, 2, 6, 4};
   const int grid = sm_count() * 3;
   const int n_partials = sm_count() * 6;     // row length of ss_partials (>= every grid used here)
   const int grid_v = sm_count() * kBlocksPerSm[cfg];
@@ -452,6 +548,10 @@ int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* la
     case 1: ES_LAUNCH(OPT, 2, 4); break;               \
     case 2: ES_LAUNCH(OPT, 4, 2); break;               \
     case 3: ES_LAUNCH(OPT, 2, 6); break;               \
+    case 4: ES_LAUNCH(OPT, 2, 3); break;               \
+    case 5: ES_LAUNCH(OPT, 2, 2); break;               \
+    case 6: ES_LAUNCH(OPT, 1, 6); break;               \
+    case 7: ES_LAUNCH(OPT, 1, 4); break;               \
     default: ES_LAUNCH(OPT, 4, 3); break;              \
   }
     CTR_OPT_SWITCH(opt, ES_CALL)

@@ -391,6 +391,14 @@ def epoch_reg_loss(ss_rows, ss_partials, n_partials, upto, scale, reg, accumulat
         "ctr_epoch_reg_loss")
 
 
+def selftest_divsqrt(seed: int, n: int, device) -> tuple:
+    """(sqrt mismatches, div mismatches) of the sweeps' in-range IEEE fast paths vs sqrt.rn / div.rn on n operands"""
+    mism = torch.zeros(2, dtype=torch.int64, device=device)
+    check(_L.ctr_selftest_divsqrt(int(seed), int(n), _p(mism, torch.int64, "mismatches"), _stream()),
+          "ctr_selftest_divsqrt")
+    return tuple(int(x) for x in mism.tolist())
+
+
 def reduce_sum(inp, scale, out, ws):
     check(
         _L.ctr_reduce_sum(_p(inp, torch.float32, "in"), inp.numel(), float(scale), _p(out, torch.float32, "out"),
