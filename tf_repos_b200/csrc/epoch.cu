@@ -44,32 +44,44 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
   __syncthreads();
   const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int c = threadIdx.x % LPR;
+  const int lane = threadIdx.x & 31;
   const bool active = u < n_max && u < n_uniq[0];
-  int64_t id = 0;
-  bool wrote = false;
-  if (active) {
-    Hyper h = load_hyper(hyper);
-    id = uniq[u];
-    const int l0 = last[id];
-    const int64_t row = id * K;
-    float4 x[VEC], a[VEC], b[VEC];
+  Hyper h = load_hyper(hyper);
+  const AdamConsts ac = adam_consts(h);
+  const int64_t id = active ? uniq[u] : 0;
+  const int l0 = active ? last[id] : j;
+  const int64_t row = id * K;
+  float4 x[VEC], a[VEC], b[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const int64_t e = row + (c + v * LPR) * 4;
-      x[v] = *reinterpret_cast<const float4*>(var + e);
-      a[v] = *reinterpret_cast<const float4*>(slot0 + e);
-      b[v] = two ? *reinterpret_cast<const float4*>(slot1 + e) : f4_zero();
-    }
-    for (int s = l0; s < j; ++s) {
-      h.lr = lr_table[s];
-      float q = 0.f;
+  for (int v = 0; v < VEC; ++v) {
+    const int64_t e = row + (c + v * LPR) * 4;
+    x[v] = active ? *reinterpret_cast<const float4*>(var + e) : f4_zero();
+    a[v] = active ? *reinterpret_cast<const float4*>(slot0 + e) : f4_zero();
+    b[v] = (active && two) ? *reinterpret_cast<const float4*>(slot1 + e) : f4_zero();
+  }
+  // warp-uniform trip count (the body reduces across the warp); a lane joins at its own row's `last`
+  const int lmin = __reduce_min_sync(FULL_MASK, l0);
+#pragma unroll 1
+  for (int s = lmin; s < j; ++s) {
+    h.lr = lr_table[s];
+    float q = 0.f;
+    if (s >= l0) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) { q += sq4(x[v]); step_untouched4<OPT>(x[v], a[v], b[v], h); }
-      atomicAdd(&ss_blk[s], q);
+      for (int v = 0; v < VEC; ++v) q += sq4(x[v]);
+      if (OPT == CTR_OPT_ADAM) {
+        adam_untouched<VEC>(x, a, b, h, ac);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) step_untouched4<OPT>(x[v], a[v], b[v], h);
+      }
     }
-    if (APPLY) {
-      h.lr = lr_table[j];
-      float q = 0.f;
+    q = warp_sum(q);
+    if (lane == 0 && q != 0.f) atomicAdd(&ss_blk[s], q);
+  }
+  if (APPLY) {
+    h.lr = lr_table[j];
+    float q = 0.f;
+    if (active) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         q += sq4(x[v]);
@@ -78,17 +90,18 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
                         __fadd_rn(g.z, __fmul_rn(h.l2, x[v].z)), __fadd_rn(g.w, __fmul_rn(h.l2, x[v].w)));
         step_sparse4<OPT>(x[v], a[v], b[v], g, h);
       }
-      atomicAdd(&ss_blk[j], q);
     }
-    if (APPLY || l0 < j) {
+    q = warp_sum(q);
+    if (lane == 0 && q != 0.f) atomicAdd(&ss_blk[j], q);
+  }
+  const bool wrote = active && (APPLY || l0 < j);
+  if (wrote) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const int64_t e = row + (c + v * LPR) * 4;
-        *reinterpret_cast<float4*>(var + e) = x[v];
-        *reinterpret_cast<float4*>(slot0 + e) = a[v];
-        if (two) *reinterpret_cast<float4*>(slot1 + e) = b[v];
-      }
-      wrote = true;
+    for (int v = 0; v < VEC; ++v) {
+      const int64_t e = row + (c + v * LPR) * 4;
+      *reinterpret_cast<float4*>(var + e) = x[v];
+      *reinterpret_cast<float4*>(slot0 + e) = a[v];
+      if (two) *reinterpret_cast<float4*>(slot1 + e) = b[v];
     }
   }
   __syncthreads();  // every lane of a row has read `last` before lane 0 of the row rewrites it
@@ -111,31 +124,43 @@ epoch_rows_generic_kernel(float* __restrict__ var, float* __restrict__ slot0, fl
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t u = t / K;
   const int k = (int)(t % K);
-  if (u < n_max && u < n_uniq[0]) {
-    Hyper h = load_hyper(hyper);
-    const int64_t id = uniq[u];
-    const int l0 = last[id];
-    const int64_t e = id * K + k;
-    float x = var[e], a = slot0[e], b = two ? slot1[e] : 0.f;
-    for (int s = l0; s < j; ++s) {
-      h.lr = lr_table[s];
-      atomicAdd(&ss_blk[s], x * x);
+  const int lane = threadIdx.x & 31;
+  const bool active = u < n_max && u < n_uniq[0];
+  Hyper h = load_hyper(hyper);
+  const int64_t id = active ? uniq[u] : 0;
+  const int l0 = active ? last[id] : j;
+  const int64_t e = id * K + k;
+  float x = active ? var[e] : 0.f, a = active ? slot0[e] : 0.f, b = (active && two) ? slot1[e] : 0.f;
+  const int lmin = __reduce_min_sync(FULL_MASK, l0);   // warp-uniform trip count, lanes join at their own `last`
+#pragma unroll 1
+  for (int s = lmin; s < j; ++s) {
+    h.lr = lr_table[s];
+    float q = 0.f;
+    if (s >= l0) {
+      q = x * x;
       step_sparse<OPT>(x, a, b, __fmul_rn(h.l2, x), h);
     }
-    if (APPLY) {
-      h.lr = lr_table[j];
-      atomicAdd(&ss_blk[j], x * x);
+    q = warp_sum(q);
+    if (lane == 0 && q != 0.f) atomicAdd(&ss_blk[s], q);
+  }
+  if (APPLY) {
+    h.lr = lr_table[j];
+    float q = 0.f;
+    if (active) {
+      q = x * x;
       step_sparse<OPT>(x, a, b, __fadd_rn(g_uniq[u * K + k], __fmul_rn(h.l2, x)), h);
     }
-    if (APPLY || l0 < j) {
-      var[e] = x; slot0[e] = a;
-      if (two) slot1[e] = b;
-    }
+    q = warp_sum(q);
+    if (lane == 0 && q != 0.f) atomicAdd(&ss_blk[j], q);
+  }
+  if (active && (APPLY || l0 < j)) {
+    var[e] = x; slot0[e] = a;
+    if (two) slot1[e] = b;
   }
   // the row's `last` byte is written after every k of the row has read it; the host wrapper only
   // admits K that divide 256 here, so a row never straddles two CTAs
   __syncthreads();
-  if (u < n_max && u < n_uniq[0] && k == 0) last[uniq[u]] = (uint8_t)(APPLY ? j + 1 : j);
+  if (active && k == 0) last[id] = (uint8_t)(APPLY ? j + 1 : j);
   if (threadIdx.x < EPOCH_MAX && ss_blk[threadIdx.x] != 0.f) atomicAdd(&ss[threadIdx.x], (double)ss_blk[threadIdx.x]);
 }
 

@@ -32,7 +32,10 @@ class TimedLib:
             e0.record()
             r = fn(*a)
             e1.record()
-            self.records.append((name, e0, e1))
+            key = name
+            if name == "ctr_epoch_rows":   # (opt, apply, ..., K at 10, ..., j at 13)
+                key = f"{name}[apply={a[1]},K={a[10]},j={'lo' if a[13] < 8 else 'hi'}]"
+            self.records.append((key, e0, e1))
             return r
         return call
 
