@@ -8,24 +8,23 @@
 // SIMT pipe).
 //
 // Structure of one CTA (128 threads, one 128 x BN output tile, BN <= 128):
-//   loop over 32-wide reduction slices, 2-stage ring:
-//     all threads : global -> registers (any operand orientation; the gather transposes for free)
+//   loop over 32-wide reduction slices, 2-stage ring (1 stage when the reduction is a single slice):
+//     all threads : registers (loaded one slice ahead, coalesced for either operand orientation)
 //                   -> hi/lo split -> st.shared in the canonical K-major SWIZZLE_128B UMMA layout
-//                   fence.proxy.async ; __syncthreads
+//                   fence.proxy.async ; __syncthreads ; issue the NEXT slice's global loads
 //     thread 0    : 4 k-steps x 3 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) ;
 //                   tcgen05.commit -> mbarrier of the stage (frees it for the refill two slices later)
-//   epilogue      : tcgen05.ld 32x32b (thread t owns accumulator row t) -> bias / group bias / relu /
-//                   dropout / accumulate -> global
+//   epilogue      : tcgen05.ld 32x32b (thread t owns accumulator row t) -> staging tile in shared memory ->
+//                   whole rows per warp: bias / group bias / relu / dropout / accumulate -> 512 B coalesced stores
 // Operands are staged by plain loads rather than TMA because the three products of a layer need
 // three different operand orientations of fp32 data that must be split anyway.
 #include "common.cuh"
 
 namespace ctr {
 
-constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 2;
+constexpr int TC_BM = 128, TC_BK = 32;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB: one 128 x 32 fp32 operand tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -88,18 +87,78 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
+// ---- operand staging -----------------------------------------------------------------------------------------
+// One 128 x 32 fp32 operand tile = 8 float4 per thread.  RC (the reduction index is the contiguous one in
+// global memory): a warp reads 4 rows x 128 B per instruction (8 lanes per row) -- coalesced -- and the same
+// (row, 16-byte chunk) assignment makes the swizzled shared-memory stores conflict-free.  !RC (the tile row
+// index is the contiguous one): thread t owns tile row t, consecutive threads read consecutive addresses.
+template <bool RC>
+__device__ __forceinline__ void load_tile(float4 (&r)[8], const float* __restrict__ P, int ld, int row0, int n_rows,
+                                          int r0, int r_end, int tid) {
+  if (RC) {
+    const int sub = (tid & 31) >> 3, ch = tid & 7, wrow = (tid >> 5) * 32;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int g = row0 + wrow + it * 4 + sub, k0 = r0 + ch * 4;
+      const float* p = P + (int64_t)g * ld + k0;
+      if (g < n_rows && k0 + 4 <= r_end && ((((uintptr_t)p) & 15) == 0)) {
+        r[it] = __ldg(reinterpret_cast<const float4*>(p));
+      } else {
+        const bool in = g < n_rows;
+        r[it].x = (in && k0 < r_end) ? p[0] : 0.f;
+        r[it].y = (in && k0 + 1 < r_end) ? p[1] : 0.f;
+        r[it].z = (in && k0 + 2 < r_end) ? p[2] : 0.f;
+        r[it].w = (in && k0 + 3 < r_end) ? p[3] : 0.f;
+      }
+    }
+  } else {
+    const int g = row0 + tid;
+    const bool in = g < n_rows;
+    const float* p = P + (int64_t)r0 * ld + g;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      r[c].x = (in && r0 + 4 * c < r_end) ? p[(int64_t)(4 * c) * ld] : 0.f;
+      r[c].y = (in && r0 + 4 * c + 1 < r_end) ? p[(int64_t)(4 * c + 1) * ld] : 0.f;
+      r[c].z = (in && r0 + 4 * c + 2 < r_end) ? p[(int64_t)(4 * c + 2) * ld] : 0.f;
+      r[c].w = (in && r0 + 4 * c + 3 < r_end) ? p[(int64_t)(4 * c + 3) * ld] : 0.f;
+    }
+  }
+}
+
+// hi/lo split + store into the K-major SWIZZLE_128B tiles
+template <bool RC>
+__device__ __forceinline__ void store_tile(const float4 (&r)[8], uint8_t* hi_tile, uint8_t* lo_tile, int tid) {
+  const int sub = (tid & 31) >> 3, ch = tid & 7, wrow = (tid >> 5) * 32;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = RC ? (wrow + it * 4 + sub) : tid;
+    const int chunk = RC ? ch : it;
+    float4 hi, lo;
+    hi.x = tf32_hi(r[it].x); hi.y = tf32_hi(r[it].y); hi.z = tf32_hi(r[it].z); hi.w = tf32_hi(r[it].w);
+    lo.x = r[it].x - hi.x; lo.y = r[it].y - hi.y; lo.z = r[it].z - hi.z; lo.w = r[it].w - hi.w;
+    const uint32_t off = sw128_off(row, chunk);
+    *reinterpret_cast<float4*>(hi_tile + off) = hi;
+    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+  }
+}
+
+constexpr int TC_STG_PITCH = TC_BM + 4;                          // epilogue staging row pitch (floats)
+constexpr int TC_STG_BYTES = TC_BM * TC_STG_PITCH * 4;
+constexpr int tc_smem_bytes(int stages) { return (stages * TC_STAGE_BYTES > TC_STG_BYTES ? stages * TC_STAGE_BYTES : TC_STG_BYTES) + 1024; }
+
 // C[i][j] = sum_r A(i,r) * B(r,j)
 //   A_RC: A(i,r) = A[i*lda + r] else A[r*lda + i];  B_RC: B(r,j) = B[j*ldb + r] else B[r*ldb + j]
 // EPI 0: store (split-R chunk z to C + z*M*ldc)  1: act(acc + bias + gbias[i/gP]) (/keep*mask)  2: C += acc
-template <bool A_RC, bool B_RC, int EPI>
-__global__ void __launch_bounds__(128, 1)
+// STAGES: depth of the operand ring (1 when the reduction fits one 32-wide slice: two CTAs per SM then)
+template <bool A_RC, bool B_RC, int EPI, int STAGES>
+__global__ void __launch_bounds__(128)
 tc_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C,
                int ldc, int M, int N, int R, const float* __restrict__ bias, int act, const float* __restrict__ mask,
                float keep, const float* __restrict__ gbias, int gP) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_stage[TC_STAGES];
+  __shared__ uint64_t bar_stage[STAGES];
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B wants 1024 B alignment
   const int i0 = blockIdx.y * TC_BM, j0 = blockIdx.x * TC_BM;
   const int n_here = min(N - j0, TC_BM);
@@ -109,12 +168,18 @@ tc_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
   const int KT = (r_end - r_begin + TC_BK - 1) / TC_BK;
 
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) mbar_init(&bar_stage[s], 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bar_stage[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {   // TMEM: 2 x 128 columns x 128 lanes of fp32 accumulators (main | small terms)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // the first slice's global loads fly while the TMEM allocation settles
+  float4 ra[8], rb[8];
+  if (KT > 0) {
+    load_tile<A_RC>(ra, A, lda, i0, M, r_begin, r_end, tid);
+    load_tile<B_RC>(rb, B, ldb, j0, N, r_begin, r_end, tid);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -123,71 +188,21 @@ tc_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
   const uint32_t idesc = make_idesc(TC_BM, n_pad);
 
   for (int kt = 0; kt < KT; ++kt) {
-    const int s = kt % TC_STAGES;
-    if (kt >= TC_STAGES) {   // the MMAs that read this stage two slices ago must be done
-      mbar_wait(&bar_stage[s], (uint32_t)(((kt / TC_STAGES) - 1) & 1));
+    const int s = kt % STAGES;
+    if (kt >= STAGES) {   // the MMAs that read this stage STAGES slices ago must be done
+      mbar_wait(&bar_stage[s], (uint32_t)(((kt / STAGES) - 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     uint8_t* st = smem + s * TC_STAGE_BYTES;
-    const int r0 = r_begin + kt * TC_BK;
-    // ---- operand A: thread t stages row i0+t ----
-    {
-      float v[TC_BK];
-      const int gi = i0 + tid;
-      if (A_RC) {
-        const float* p = A + (int64_t)gi * lda + r0;
-        const bool full = gi < M && r0 + TC_BK <= r_end && ((((uintptr_t)p) & 15) == 0);
-        if (full) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) { const float4 t = *reinterpret_cast<const float4*>(p + 4 * c); v[4*c] = t.x; v[4*c+1] = t.y; v[4*c+2] = t.z; v[4*c+3] = t.w; }
-        } else {
-#pragma unroll
-          for (int k = 0; k < TC_BK; ++k) v[k] = (gi < M && r0 + k < r_end) ? p[k] : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < TC_BK; ++k) v[k] = (gi < M && r0 + k < r_end) ? A[(int64_t)(r0 + k) * lda + gi] : 0.f;
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 hi, lo;
-        hi.x = tf32_hi(v[4*c]); hi.y = tf32_hi(v[4*c+1]); hi.z = tf32_hi(v[4*c+2]); hi.w = tf32_hi(v[4*c+3]);
-        lo.x = v[4*c] - hi.x; lo.y = v[4*c+1] - hi.y; lo.z = v[4*c+2] - hi.z; lo.w = v[4*c+3] - hi.w;
-        const uint32_t off = sw128_off(tid, c);
-        *reinterpret_cast<float4*>(st + off) = hi;
-        *reinterpret_cast<float4*>(st + TC_TILE_BYTES + off) = lo;
-      }
-    }
-    // ---- operand B: thread t stages output column j0+t ----
-    if (tid < n_pad) {
-      float v[TC_BK];
-      const int gj = j0 + tid;
-      if (B_RC) {
-        const float* p = B + (int64_t)gj * ldb + r0;
-        const bool full = gj < N && r0 + TC_BK <= r_end && ((((uintptr_t)p) & 15) == 0);
-        if (full) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) { const float4 t = *reinterpret_cast<const float4*>(p + 4 * c); v[4*c] = t.x; v[4*c+1] = t.y; v[4*c+2] = t.z; v[4*c+3] = t.w; }
-        } else {
-#pragma unroll
-          for (int k = 0; k < TC_BK; ++k) v[k] = (gj < N && r0 + k < r_end) ? p[k] : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < TC_BK; ++k) v[k] = (gj < N && r0 + k < r_end) ? B[(int64_t)(r0 + k) * ldb + gj] : 0.f;
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 hi, lo;
-        hi.x = tf32_hi(v[4*c]); hi.y = tf32_hi(v[4*c+1]); hi.z = tf32_hi(v[4*c+2]); hi.w = tf32_hi(v[4*c+3]);
-        lo.x = v[4*c] - hi.x; lo.y = v[4*c+1] - hi.y; lo.z = v[4*c+2] - hi.z; lo.w = v[4*c+3] - hi.w;
-        const uint32_t off = sw128_off(tid, c);
-        *reinterpret_cast<float4*>(st + 2 * TC_TILE_BYTES + off) = hi;
-        *reinterpret_cast<float4*>(st + 3 * TC_TILE_BYTES + off) = lo;
-      }
-    }
+    store_tile<A_RC>(ra, st, st + TC_TILE_BYTES, tid);
+    store_tile<B_RC>(rb, st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, tid);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     __syncthreads();
+    if (kt + 1 < KT) {   // next slice: global -> registers while the tensor core works on this one
+      const int r0 = r_begin + (kt + 1) * TC_BK;
+      load_tile<A_RC>(ra, A, lda, i0, M, r0, r_end, tid);
+      load_tile<B_RC>(rb, B, ldb, j0, N, r0, r_end, tid);
+    }
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_TILE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
@@ -206,13 +221,13 @@ tc_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
     }
   }
   if (KT > 0) {   // the last commit tracks every MMA issued before it
-    mbar_wait(&bar_stage[(KT - 1) % TC_STAGES], (uint32_t)(((KT - 1) / TC_STAGES) & 1));
+    mbar_wait(&bar_stage[(KT - 1) % STAGES], (uint32_t)(((KT - 1) / STAGES) & 1));
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // ---- epilogue: thread t <-> accumulator row t (TMEM lane 32*warp + lane) ----
-  const int gi = i0 + tid;
-  float* Cz = C + (EPI == 0 ? (int64_t)blockIdx.z * M * ldc : 0);
+  // ---- epilogue 1: TMEM -> registers (thread t <-> accumulator row t) -> staging tile in shared memory
+  // (the operand stages are free: every MMA that read them has completed)
+  float* stg = reinterpret_cast<float*>(smem);
   for (int c0 = 0; c0 < n_pad; c0 += 16) {
     uint32_t r[16], r2[16];
     if (KT > 0) {
@@ -234,42 +249,92 @@ tc_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
 #pragma unroll
       for (int q = 0; q < 16; ++q) r[q] = 0u;
     }
-    if (gi < M) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int gj = j0 + c0 + q;
-        if (gj < N) {
-          float v = __uint_as_float(r[q]);
-          if (EPI == 2) v += Cz[(int64_t)gi * ldc + gj];
-          if (EPI == 1) {
-            if (bias) v += bias[gj];
-            if (gbias) v += gbias[(int64_t)(gi / gP) * N + gj];
-            if (act == 1) v = fmaxf(v, 0.f);
-            if (mask) v = __fdiv_rn(v, keep) * mask[(int64_t)gi * ldc + gj];
-          }
-          Cz[(int64_t)gi * ldc + gj] = v;
-        }
-      }
-    }
+    for (int q = 0; q < 16; q += 4)
+      *reinterpret_cast<uint4*>(stg + tid * TC_STG_PITCH + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256));
+
+  // ---- epilogue 2: a warp writes whole rows (lane l <-> columns 4l..4l+3): 512 B coalesced stores
+  float* Cz = C + (EPI == 0 ? (int64_t)blockIdx.z * M * ldc : 0);
+  const int col = lane * 4, gj = j0 + col;
+  const bool vec = ((ldc & 3) == 0) && ((((uintptr_t)Cz) & 15) == 0) && (EPI != 1 || !mask || ((((uintptr_t)mask) & 15) == 0));
+  if (col < n_here) {
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (EPI == 1 && bias) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bv[q] = (gj + q < N) ? bias[gj + q] : 0.f;
+    }
+    const int rows = min(TC_BM, M - i0);
+    for (int row = warp; row < rows; row += 4) {
+      const int gi = i0 + row;
+      const float4 t = *reinterpret_cast<const float4*>(stg + row * TC_STG_PITCH + col);
+      float v[4] = {t.x, t.y, t.z, t.w};
+      float* cp = Cz + (int64_t)gi * ldc + gj;
+      const bool full = vec && (col + 4 <= n_here);
+      if (EPI == 2) {
+        if (full) { const float4 o = *reinterpret_cast<const float4*>(cp); v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
+        else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (col + q < n_here) v[q] += cp[q];
+        }
+      }
+      if (EPI == 1) {
+        const float* gb = gbias ? gbias + (int64_t)(gi / gP) * N + gj : nullptr;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[q] += bv[q];
+          if (gb && col + q < n_here) v[q] += gb[q];
+          if (act == 1) v[q] = fmaxf(v[q], 0.f);
+        }
+        if (mask) {
+          const float* mp = mask + (int64_t)gi * ldc + gj;
+          if (full) {
+            const float4 mk = *reinterpret_cast<const float4*>(mp);
+            v[0] = __fdiv_rn(v[0], keep) * mk.x; v[1] = __fdiv_rn(v[1], keep) * mk.y;
+            v[2] = __fdiv_rn(v[2], keep) * mk.z; v[3] = __fdiv_rn(v[3], keep) * mk.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (col + q < n_here) v[q] = __fdiv_rn(v[q], keep) * mp[q];
+          }
+        }
+      }
+      if (full) {
+        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (col + q < n_here) cp[q] = v[q];
+      }
+    }
+  }
+}
+
+template <bool A_RC, bool B_RC, int EPI, int STAGES>
+static int launch_tc_s(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int R, int S,
+                       const float* bias, int act, const float* mask, float keep, const float* gbias, int gP,
+                       cudaStream_t st) {
+  static bool attr = false;
+  constexpr int smem = tc_smem_bytes(STAGES);
+  if (!attr) {
+    cudaFuncSetAttribute(tc_gemm_kernel<A_RC, B_RC, EPI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  dim3 grid((N + TC_BM - 1) / TC_BM, (M + TC_BM - 1) / TC_BM, S);
+  tc_gemm_kernel<A_RC, B_RC, EPI, STAGES><<<grid, 128, smem, st>>>(A, lda, B, ldb, C, ldc, M, N, R, bias, act, mask, keep,
+                                                                    gbias, gP);
+  return 0;
 }
 
 template <bool A_RC, bool B_RC, int EPI>
 static int launch_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int R, int S,
                      const float* bias, int act, const float* mask, float keep, const float* gbias, int gP,
                      cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(tc_gemm_kernel<A_RC, B_RC, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    attr = true;
-  }
-  dim3 grid((N + TC_BM - 1) / TC_BM, (M + TC_BM - 1) / TC_BM, S);
-  tc_gemm_kernel<A_RC, B_RC, EPI><<<grid, 128, TC_SMEM_BYTES, st>>>(A, lda, B, ldb, C, ldc, M, N, R, bias, act, mask, keep,
-                                                                    gbias, gP);
-  return 0;
+  const int r_chunk = (R + S - 1) / S;
+  if (r_chunk <= TC_BK)
+    return launch_tc_s<A_RC, B_RC, EPI, 1>(A, lda, B, ldb, C, ldc, M, N, R, S, bias, act, mask, keep, gbias, gP, st);
+  return launch_tc_s<A_RC, B_RC, EPI, 2>(A, lda, B, ldb, C, ldc, M, N, R, S, bias, act, mask, keep, gbias, gP, st);
 }
 
 // entry used by fc.cu: kind 0 = forward (A_RC, !B_RC, EPI 1), 1 = dIn (A_RC, B_RC, EPI 0 / 2), 2 = dW (!A_RC, !B_RC, EPI 0)
