@@ -305,6 +305,19 @@ int64_t ctr_parse_libsvm(const char* buf_host, size_t len, int F, int64_t max_ro
                          int32_t* ids_host, float* vals_host, float* labels_host, size_t* consumed_host);
 int ctr_libsvm_count_fields(const char* buf_host, size_t len);
 
+/* ---- libsvm input (DEVICE buffers) -----------------------------------------------------
+ * The same decode_libsvm (DeepFM.py:65-81) for text that is already in device memory: the first max_rows
+ * complete lines of text[0,len) (plus an unterminated last line when final_chunk != 0) are tokenised by one
+ * thread each.  Every value this path emits has exactly the bits ctr_parse_libsvm (strtof/strtol) gives;
+ * whatever it cannot guarantee is only COUNTED and the caller re-parses the chunk with the host entry point:
+ *   info (device int64[5]) = { rows, bytes consumed, blank lines, malformed lines (bad token / pair count != F),
+ *                             lines holding a number for the host (inf/nan/hex, > 15 digits, |exp10| > 22,
+ *                             fp32 subnormal/overflow, or within one double-ulp of an fp32 rounding boundary) }
+ * ids/vals/labels rows are valid iff info[2] == info[3] == info[4] == 0.  len < 2^32. */
+size_t ctr_parse_libsvm_device_workspace_bytes(size_t len, int64_t max_rows);
+int ctr_parse_libsvm_device(const char* text, size_t len, int F, int64_t max_rows, int final_chunk, int32_t* ids,
+                            float* vals, float* labels, int64_t* info, void* ws, size_t ws_bytes, ctr_stream_t stream);
+
 /* ---- table initialisation (glorot_normal_initializer, DeepFM.py:115-116; truncated at 2 sigma) --- */
 int ctr_init_trunc_normal(float* t, int64_t n, float stddev, uint64_t seed, ctr_stream_t stream);
 int ctr_fill(float* t, int64_t n, float value, ctr_stream_t stream);

@@ -110,7 +110,9 @@ def run(build_model: Callable[[], object], model_name: str):
     F = FLAGS.field_size
 
     def batches(files, epochs):
-        for feats, labels in input_fn(files, num_epochs=epochs, batch_size=FLAGS.batch_size, field_size=F):
+        parse_dev = dev if getattr(FLAGS, "input_parse", "device") == "device" else None
+        for feats, labels in input_fn(files, num_epochs=epochs, batch_size=FLAGS.batch_size, field_size=F,
+                                      device=parse_dev):
             yield (feats["feat_ids"].reshape(-1, F).to(dev, non_blocking=True),
                    feats["feat_vals"].reshape(-1, F).to(dev, non_blocking=True), labels.to(dev, non_blocking=True))
 

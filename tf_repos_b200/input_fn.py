@@ -71,14 +71,74 @@ def decode_libsvm_file(path: str, field_size: int = 0, threads: int = 10):
             np.concatenate([p[2] for p in parts]))
 
 
+def decode_libsvm_file_device(path: str, field_size: int = 0, device="cuda", chunk_bytes: int = 256 << 20):
+    """Whole file -> (ids, vals, labels) as CUDA tensors, tokenised on the GPU (ctr_parse_libsvm_device): the file
+    is read in chunks cut at line ends, copied to the device and parsed there; a chunk the device parser
+    declines (blank/malformed line, a number only strtof may decide) is re-parsed by the host parser, so results and
+    error messages are exactly those of decode_libsvm_file."""
+    from . import ops
+    with open(path, "rb") as fh:
+        data = fh.read()
+    F = field_size or _L.ctr_libsvm_count_fields(data, len(data))
+    dev = torch.device(device)
+    if F <= 0 or len(data) == 0:
+        return (torch.empty(0, max(field_size, 0), dtype=torch.int32, device=dev),
+                torch.empty(0, max(field_size, 0), dtype=torch.float32, device=dev),
+                torch.empty(0, dtype=torch.float32, device=dev))
+    parts = []
+    pos, n = 0, len(data)
+    while pos < n:
+        end = min(n, pos + chunk_bytes)
+        if end < n:
+            nl = data.find(b"\n", end)
+            end = n if nl < 0 else nl + 1
+        raw = np.frombuffer(data, dtype=np.uint8, count=end - pos, offset=pos)
+        text = torch.from_numpy(raw.copy()).to(dev, non_blocking=False)
+        max_rows = max(1, (end - pos) // max(2 * F + 2, 1))
+        ids, vals, labels, consumed, needs_host = ops.parse_libsvm_device(text, F, max_rows, final_chunk=True)
+        if needs_host or consumed != end - pos:
+            h = _parse(data, pos, end, F)
+            ids, vals, labels = (torch.from_numpy(a.copy()).to(dev) for a in h)
+        parts.append((ids, vals, labels))
+        pos = end
+    if len(parts) == 1:
+        return parts[0]
+    return tuple(torch.cat([p[k] for p in parts]) for k in range(3))
+
+
 def _pin(t: torch.Tensor) -> torch.Tensor:
     return t.pin_memory() if torch.cuda.is_available() else t
 
 
+def _input_fn_device(files, batch_size, num_epochs, field_size, device):
+    """Same batching (repeat before batch, last partial batch kept), tensors tokenised on and left on the GPU."""
+    carry = None
+    for _ in range(num_epochs):
+        for path in files:
+            ids, vals, labels = decode_libsvm_file_device(path, field_size, device)
+            if carry is not None:
+                ids, vals, labels = (torch.cat([c, t]) for c, t in zip(carry, (ids, vals, labels)))
+                carry = None
+            n_full = (labels.shape[0] // batch_size) * batch_size
+            for lo in range(0, n_full, batch_size):
+                hi = lo + batch_size
+                yield ({"feat_ids": ids[lo:hi].unsqueeze(-1), "feat_vals": vals[lo:hi].unsqueeze(-1)}, labels[lo:hi])
+            if n_full < labels.shape[0]:
+                carry = (ids[n_full:], vals[n_full:], labels[n_full:])
+    if carry is not None and carry[2].shape[0]:
+        yield ({"feat_ids": carry[0].unsqueeze(-1), "feat_vals": carry[1].unsqueeze(-1)}, carry[2])
+
+
 def input_fn(filenames: Union[str, Sequence[str]], batch_size: int = 32, num_epochs: int = 1,
-             perform_shuffle: bool = False, field_size: int = 0) -> Iterator[Tuple[Dict[str, torch.Tensor], torch.Tensor]]:
+             perform_shuffle: bool = False, field_size: int = 0,
+             device=None) -> Iterator[Tuple[Dict[str, torch.Tensor], torch.Tensor]]:
+    """device=None: host parser, pinned host tensors.  device="cuda[:i]": the text is copied to the GPU and
+    tokenised there (ctr_parse_libsvm_device); batches are CUDA tensors.  Identical values either way."""
     print("Parsing", filenames)  # DeepFM.py:64
     files = [filenames] if isinstance(filenames, str) else list(filenames)
+    if device is not None and not perform_shuffle:
+        yield from _input_fn_device(files, batch_size, num_epochs, field_size, device)
+        return
 
     def rows():
         for _ in range(num_epochs):

@@ -424,6 +424,25 @@ def logit_loss(bias, y_a, y_b, y_c, labels, B, y=None, pred=None, loss_ce=None, 
         "ctr_logit_loss")
 
 
+def parse_libsvm_device(text: torch.Tensor, F: int, max_rows: int, final_chunk: bool = True):
+    """decode_libsvm (DeepFM.py:65-81) on a uint8 CUDA tensor of text.  Returns (ids int32 [rows,F], vals f32 [rows,F],
+    labels f32 [rows], consumed bytes, needs_host) -- when needs_host is True the chunk holds something only the host
+    parser may decide (blank/malformed line, exotic number) and the outputs must be discarded."""
+    assert text.is_cuda and text.dtype == torch.uint8 and text.is_contiguous()
+    dev, n = text.device, text.numel()
+    ids = torch.empty(max_rows, F, dtype=torch.int32, device=dev)
+    vals = torch.empty(max_rows, F, dtype=torch.float32, device=dev)
+    labels = torch.empty(max_rows, dtype=torch.float32, device=dev)
+    info = torch.empty(5, dtype=torch.int64, device=dev)
+    ws_bytes = int(_L.ctr_parse_libsvm_device_workspace_bytes(n, max_rows))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(_L.ctr_parse_libsvm_device(text.data_ptr(), n, F, max_rows, int(final_chunk), ids.data_ptr(), vals.data_ptr(),
+                                     labels.data_ptr(), info.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+          "ctr_parse_libsvm_device")
+    rows, consumed, blank, bad, host = (int(x) for x in info.tolist())
+    return ids[:rows], vals[:rows], labels[:rows], consumed, bool(blank or bad or host)
+
+
 def init_trunc_normal(t, stddev: float, seed: int):
     check(_L.ctr_init_trunc_normal(_p(t, torch.float32, "t"), t.numel(), float(stddev), int(seed), _stream()),
           "ctr_init_trunc_normal")
