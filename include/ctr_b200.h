@@ -191,7 +191,7 @@ int ctr_selftest_divsqrt(uint64_t seed, int64_t n, int64_t* mismatches, ctr_stre
 /* ---- loss head -----------------------------------------------------------------------------------
  * y = ((bias + y_a) + y_b) + y_c (NULL terms skipped; DeepFM.py:172-175), pred = sigmoid(y)
  * (:176), loss_ce = sum(max(y,0) - y*t + log1p(exp(-|y|)))/B_total (:188), dy = (pred - t)/B_total,
- * dbias = sum(dy).  B_total = B on one GPU; the global batch under data parallelism (the per-rank
+ * dbias = sum(dy).  B_total = B on one GPU; 1 = summed loss (canned estimators); the global batch under data parallelism (the per-rank
  * loss_ce / dbias / gradients then SUM to the global mean).  labels NULL => inference (y, pred only).
  */
 int ctr_logit_loss(const float* bias, const float* y_a, const float* y_b, const float* y_c,
@@ -296,6 +296,21 @@ int ctr_a2a_bucket_ids(const int32_t* uniq, const int32_t* n_uniq, int64_t n_max
                        int32_t* cursor, int32_t* order, int32_t* pos_of, int32_t* local_ids, ctr_stream_t stream);
 int ctr_remap_ids(const int32_t* inverse, const int32_t* pos_of, int64_t n, int32_t* out, ctr_stream_t stream);
 int ctr_gather_scalar(const int32_t* ids, const float* W, int64_t N, int64_t n, float* out, ctr_stream_t stream);
+
+/* ---- wide_n_deep feature columns (wide_n_deep.py:92-107) ------------------------------------
+ * categorical_column_with_identity(num_buckets=NB, default_value=0) + embedding_column(K) per categorical
+ * column, numeric columns appended in the name-sorted order (num_perm), and the linear_model over the same
+ * columns.  The Fc per-column tables are stacked: column f owns rows [f*NB, (f+1)*NB) of emb [Fc*NB, K] and
+ * wide_cat [Fc*NB]; flat_ids[b,f] = f*NB + (0 <= id < NB ? id : 0).
+ *   x   [B, Fc*K + Fd] = [emb rows of columns 0..Fc-1 | dense[b, num_perm[0..Fd-1]]]      (emb != NULL)
+ *   lin [B] = sum_f wide_cat[flat_ids[b,f]] + sum_j dense[b,j]*wide_num[j] + wide_bias     (wide_* != NULL)
+ * bwd: g_rows[b*Fc+f,:] = dX[b, f*K:(f+1)*K], g_cat[b*Fc+f] = dy[b], g_num[j] = sum_b dy[b]*dense[b,j],
+ *      g_bias = sum_b dy[b]  (fixed reduction trees: deterministic).  NULL outputs are skipped. */
+int ctr_wd_input_fwd(const int32_t* ids, const float* dense, const float* emb, const float* wide_cat,
+                     const float* wide_num, const float* wide_bias, const int32_t* num_perm, int B, int Fc, int Fd,
+                     int NB, int K, int32_t* flat_ids, float* x, float* lin, ctr_stream_t stream);
+int ctr_wd_input_bwd(const float* dX, const float* dy, const float* dense, int B, int Fc, int Fd, int K, float* g_rows,
+                     float* g_cat, float* g_num, float* g_bias, ctr_stream_t stream);
 
 /* ---- libsvm input (HOST buffers) -------------------------------------------------------------------
  * decode_libsvm of input_fn (DeepFM.py:65-81): "<label> <id>:<val> ..." lines -> ids int32 [rows,F],

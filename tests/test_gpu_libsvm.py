@@ -128,12 +128,12 @@ def test_input_fn_device_batches_equal_host_batches(tmp_path):
     from tf_repos_b200 import input_fn, synth
     paths = []
     for k, n in enumerate((130, 75)):
-        ids, vals, labels = synth.criteo_batch(n, 5000, 7, seed=20 + k)
+        ids, vals, labels = synth.criteo_batch(n, 5000, 15, seed=20 + k)
         p = os.path.join(tmp_path, "tr%d.libsvm" % k)
         synth.write_libsvm(p, ids, vals, labels)
         paths.append(p)
-    host = list(input_fn.input_fn(paths, batch_size=64, num_epochs=2, field_size=7))
-    dev = list(input_fn.input_fn(paths, batch_size=64, num_epochs=2, field_size=7, device="cuda"))
+    host = list(input_fn.input_fn(paths, batch_size=64, num_epochs=2, field_size=15))
+    dev = list(input_fn.input_fn(paths, batch_size=64, num_epochs=2, field_size=15, device="cuda"))
     assert len(host) == len(dev) == (2 * 205 + 63) // 64
     for (hf, hl), (df, dl) in zip(host, dev):
         assert df["feat_ids"].is_cuda and df["feat_ids"].shape == hf["feat_ids"].shape

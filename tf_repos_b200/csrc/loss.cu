@@ -67,7 +67,9 @@ using namespace ctr;
 extern "C" int ctr_logit_loss(const float* bias, const float* y_a, const float* y_b, const float* y_c,
                               const float* labels, int B, int B_total, float* y, float* pred,
                               float* loss_ce, float* dy, float* dbias, ctr_stream_t stream) {
-  CTR_REQUIRE(B >= 0 && B_total >= B, CTR_ERR_INVALID_ARG, "ctr_logit_loss: need 0 <= B <= B_total");
+  // B_total == 1 with B > 1: SUM reduction (the canned estimators' head, wide_n_deep.py)
+  CTR_REQUIRE(B >= 0 && (B_total >= B || B_total == 1), CTR_ERR_INVALID_ARG,
+              "ctr_logit_loss: need 0 <= B <= B_total (or B_total == 1 for a summed loss)");
   if (B == 0) return CTR_OK;
   CTR_REQUIRE(y_a || y_b || y_c, CTR_ERR_INVALID_ARG, "ctr_logit_loss: no logit term given");
   logit_loss_kernel<<<1, LOSS_THREADS, 0, as_stream(stream)>>>(bias, y_a, y_b, y_c, labels, B, B_total, y, pred,

@@ -25,7 +25,8 @@ class OptimizerState:
     record 2: dense variables with L2 (DCN cross_w / cross_b)
     """
 
-    def __init__(self, optimizer: str, learning_rate: float, l2_reg: float, device):
+    def __init__(self, optimizer: str, learning_rate: float, l2_reg: float, device, adagrad_init: float = 1e-8):
+        self.adagrad_init = adagrad_init   # initial_accumulator_value: 1e-8 in DeepFM.py:207, 0.1 in the canned estimators
         if optimizer not in ops.OPT_BY_NAME:
             # the reference has no branch for e.g. 'GD' although the flag help lists it (DeepFM.py:50,204-211)
             raise NameError(f"optimizer {optimizer!r} is not one of {sorted(ops.OPT_BY_NAME)}")
@@ -46,7 +47,7 @@ class OptimizerState:
 
     def slot_init(self, slot: int) -> float:
         if self.name == "Adagrad":
-            return 1e-8          # initial_accumulator_value (DeepFM.py:207)
+            return self.adagrad_init
         if self.name == "ftrl" and slot == 0:
             return 0.1           # FtrlOptimizer initial_accumulator_value default
         return 0.0

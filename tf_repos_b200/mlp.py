@@ -20,7 +20,10 @@ class MLP:
 
     def __init__(self, in_dim: int, layers: Sequence[int], keep_prob: Sequence[float], B: int, device,
                  scope: str = "Deep-part", out_scope: Optional[str] = "deep_out", out_extra_in: int = 0,
-                 seed: int = 0):
+                 seed: int = 0, layer_fmt: str = "mlp{i}", w_name: str = "weights", b_name: str = "biases"):
+        # layer_fmt / w_name / b_name: TF variable naming (contrib fully_connected: mlp{i}/weights|biases;
+        # the canned estimators' Dense layers: hiddenlayer_{i}/kernel|bias)
+        self.layer_fmt, self.w_name, self.b_name = layer_fmt, w_name, b_name
         self.in_dim, self.layers, self.keep = in_dim, list(layers), list(keep_prob)
         self.scope, self.out_scope, self.B, self.device = scope, out_scope, B, device
         # TF name of the output layer: "<scope>/<out_scope>", or out_scope itself when it is a full path
@@ -42,19 +45,25 @@ class MLP:
         self.ws = torch.empty(ws, dtype=torch.uint8, device=device)
         self._active = [None] * len(self.layers)
 
+    def _w(self, i: int) -> str:
+        return f"{self.scope}/{self.layer_fmt.format(i=i)}/{self.w_name}"
+
+    def _b(self, i: int) -> str:
+        return f"{self.scope}/{self.layer_fmt.format(i=i)}/{self.b_name}"
+
     def specs(self):
         out, d = [], self.in_dim
         for i, w in enumerate(self.layers):
-            out += [(f"{self.scope}/mlp{i}/weights", (d, w)), (f"{self.scope}/mlp{i}/biases", (w,))]
+            out += [(self._w(i), (d, w)), (self._b(i), (w,))]
             d = w
         if self.out_scope:
-            out += [(f"{self.out_name}/weights", (self.out_in, 1)), (f"{self.out_name}/biases", (1,))]
+            out += [(f"{self.out_name}/{self.w_name}", (self.out_in, 1)), (f"{self.out_name}/{self.b_name}", (1,))]
         return out
 
     def init(self, dv: DenseVars, gen: torch.Generator):
         """xavier_uniform weights, zero biases (tf.contrib.layers.fully_connected defaults)."""
         for name, shape in self.specs():
-            if name.endswith("weights"):
+            if name.endswith(self.w_name):
                 lim = (6.0 / (shape[0] + shape[1])) ** 0.5
                 w = (torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * lim
                 dv[name].copy_(w.to(torch.float32))
@@ -66,7 +75,7 @@ class MLP:
         a = x
         n = a.shape[0]
         for i in range(len(self.layers)):
-            W, b = dv[f"{self.scope}/mlp{i}/weights"], dv[f"{self.scope}/mlp{i}/biases"]
+            W, b = dv[self._w(i)], dv[self._b(i)]
             m = None
             if train and masks is not None and masks[i] is not None:
                 m = masks[i]
@@ -81,7 +90,7 @@ class MLP:
 
     def forward_out(self, a: torch.Tensor, dv: DenseVars, extra: Optional[torch.Tensor] = None) -> torch.Tensor:
         """y = [extra | a] @ W + b when `extra` is given (DCN: [x_L, x_deep]), else a @ W + b."""
-        W, b = dv[f"{self.out_name}/weights"], dv[f"{self.out_name}/biases"]
+        W, b = dv[f"{self.out_name}/{self.w_name}"], dv[f"{self.out_name}/{self.b_name}"]
         y = self.y[: a.shape[0]]
         if extra is not None:
             ops.fc1_fwd(extra, a, W.view(-1), b, y)
@@ -92,9 +101,9 @@ class MLP:
     # ---- backward ------------------------------------------------------------------------------
     def backward_out(self, a: torch.Tensor, dy: torch.Tensor, dv: DenseVars, da: torch.Tensor,
                      extra: Optional[torch.Tensor] = None):
-        W = dv[f"{self.out_name}/weights"]
-        gW = dv.grads[f"{self.out_name}/weights"].view(-1)
-        gb = dv.grads[f"{self.out_name}/biases"]
+        W = dv[f"{self.out_name}/{self.w_name}"]
+        gW = dv.grads[f"{self.out_name}/{self.w_name}"].view(-1)
+        gb = dv.grads[f"{self.out_name}/{self.b_name}"]
         if extra is not None:
             ops.fc1_bwd(extra, a, W.view(-1), dy, self.d_extra[: a.shape[0]], da, gW, gb, self.ws)
         else:
@@ -107,10 +116,10 @@ class MLP:
         if not self.layers:
             return d_last
         for i in reversed(range(len(self.layers))):
-            W = dv[f"{self.scope}/mlp{i}/weights"]
+            W = dv[self._w(i)]
             a = self.h[i - 1][:n] if i > 0 else x
             d_in = self.dh[i - 1][:n] if i > 0 else (self.dx[:n] if need_dx else None)
             ops.fc_bwd(a, W, self.h[i][:n], self._active[i], self.keep[i], d, 1, d_in,
-                       dv.grads[f"{self.scope}/mlp{i}/weights"], dv.grads[f"{self.scope}/mlp{i}/biases"], self.ws)
+                       dv.grads[self._w(i)], dv.grads[self._b(i)], self.ws)
             d = d_in
         return self.dx[:n] if need_dx else None

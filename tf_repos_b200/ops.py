@@ -424,6 +424,23 @@ def logit_loss(bias, y_a, y_b, y_c, labels, B, y=None, pred=None, loss_ce=None, 
         "ctr_logit_loss")
 
 
+def wd_input_fwd(ids, dense, emb, wide_cat, wide_num, wide_bias, num_perm, NB, K, flat_ids, x, lin):
+    B, Fc = ids.shape
+    Fd = dense.shape[1]
+    check(_L.ctr_wd_input_fwd(_p(ids, torch.int32, "ids"), _p(dense, torch.float32, "dense"), _p(emb, torch.float32, "emb"),
+                              _p(wide_cat, torch.float32, "wide_cat"), _p(wide_num, torch.float32, "wide_num"),
+                              _p(wide_bias, torch.float32, "wide_bias"), _p(num_perm, torch.int32, "num_perm"), B, Fc, Fd,
+                              NB, K, _p(flat_ids, torch.int32, "flat_ids"), _p(x, torch.float32, "x"),
+                              _p(lin, torch.float32, "lin"), _stream()), "ctr_wd_input_fwd")
+
+
+def wd_input_bwd(dX, dy, dense, B, Fc, Fd, K, g_rows, g_cat, g_num, g_bias):
+    check(_L.ctr_wd_input_bwd(_p(dX, torch.float32, "dX"), _p(dy, torch.float32, "dy"), _p(dense, torch.float32, "dense"),
+                              B, Fc, Fd, K, _p(g_rows, torch.float32, "g_rows"), _p(g_cat, torch.float32, "g_cat"),
+                              _p(g_num, torch.float32, "g_num"), _p(g_bias, torch.float32, "g_bias"), _stream()),
+          "ctr_wd_input_bwd")
+
+
 def parse_libsvm_device(text: torch.Tensor, F: int, max_rows: int, final_chunk: bool = True):
     """decode_libsvm (DeepFM.py:65-81) on a uint8 CUDA tensor of text.  Returns (ids int32 [rows,F], vals f32 [rows,F],
     labels f32 [rows], consumed bytes, needs_host) -- when needs_host is True the chunk holds something only the host
