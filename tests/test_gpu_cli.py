@@ -81,3 +81,41 @@ def test_cli_train_eval_infer_export(tmp_path, script, extra):
     sub = os.listdir(tmp + "/export")
     sig = json.load(open(os.path.join(tmp, "export", sub[0], "signature.json")))
     assert sig["inputs"]["feat_ids"] == {"dtype": "int64", "shape": [None, 39]} and "prob" in sig["outputs"]
+    # the exported model answers the serving clients' request shape (int64 ids) with pred.txt's numbers (8f-4)
+    from tf_repos_b200.input_fn import decode_libsvm_file
+    from tf_repos_b200.serving import Servable
+    ids, vals, _ = decode_libsvm_file(tmp + "/data/te.libsvm", 39)
+    s = Servable.load(os.path.join(tmp, "export", sub[0]), max_batch=64)
+    prob = s.predict(ids.astype(np.int64), vals)                      # 150 rows through a 64-row servable
+    want = np.array([float(l) for l in lines[:-1]], dtype=np.float32)
+    np.testing.assert_allclose(prob.numpy(), want, atol=1e-6)
+    one = s.predict(torch.from_numpy(ids[:1].astype(np.int64)).reshape(1, 39, 1), vals[:1])   # feat_ids[1,39] request
+    assert abs(float(one[0]) - want[0]) <= 1e-6
+
+
+@pytest.mark.parametrize("optimizer", ["Adam", "Adagrad", "ftrl"])
+def test_tf_named_training_state_roundtrip(tmp_path, optimizer):
+    """tf_names: variables + optimizer slots + beta powers + global_step under their tf.train.Saver names; a model
+    restored from the archive continues bit-identically."""
+    from tf_repos_b200 import synth, tf_names
+    from tf_repos_b200.deepfm import DeepFM
+    F, N, K, B = 39, 5000, 8, 64
+    mk = lambda: DeepFM(F, N, K, B, deep_layers="16,8", dropout="1.0,1.0", optimizer=optimizer, update_mode="exact_deferred",
+                        epoch_steps=4, device="cuda:0", seed=5)
+    a = mk()
+    batches = [synth.criteo_batch(B, N, F, seed=40 + i, device="cuda:0") for i in range(6)]
+    for b in batches[:3]:
+        a.train_step(*b)
+    sd = tf_names.state_dict_tf(a)
+    slot = {"Adam": "Adam", "Adagrad": "Adagrad", "ftrl": "Ftrl"}[optimizer]
+    assert sd["fm_v"].shape == (N, K) and sd["fm_v/" + slot].shape == (N, K) and sd["Deep-part/mlp0/weights/" + slot].shape == (F * K, 16)
+    assert int(sd["global_step"]) == 3 and (("beta1_power" in sd) == (optimizer == "Adam"))
+    path = os.path.join(str(tmp_path), "state.npz")
+    tf_names.export_npz(a, path)
+    b2 = mk()
+    tf_names.import_npz(b2, path)
+    for b in batches[3:]:
+        a.train_step(*b); b2.train_step(*b)
+    va, vb = a.variables(), b2.variables()
+    for name in va:
+        assert torch.equal(va[name], vb[name]), name
