@@ -374,9 +374,10 @@ def main_b200(args):
                          "launches_timed": len(sweep_ms), "peak_source": peak_src,
                          "kernel_share_of_step": (sum(sweep_ms) / ms_total if sweep_ms else None),
                          "note": "by design NOT HBM-bound: the kernel replays 16 optimizer steps per element in "
-                                 "registers (IEEE div+sqrt recurrence, ~36 instr/element/step) to cut HBM traffic "
-                                 "16x; its limiter is FP32 issue (see profiles/).  The HBM-bound formulation of "
-                                 "the same update is reported under exact_every_step."}}
+                                 "registers (IEEE div+sqrt recurrence, 29.5 instr/element/step against an arithmetic "
+                                 "floor of 24) to cut HBM traffic 16x; its limiter is instruction issue (77 % "
+                                 "issue-active, profiles/r01_ncu_epoch_sweep_full.txt).  The HBM-bound formulation "
+                                 "of the same update is reported under exact_every_step."}}
     if exact_sweep_ms:
         ex_avg = sum(exact_sweep_ms) / len(exact_sweep_ms)
         tr = None
