@@ -343,10 +343,11 @@ def main_b200(args):
     table_bytes = n_rows * K * 4 * 6  # Adam: read var,m,v + write var,m,v (24 B/element) per pass over the table
     sweep_avg_ms = sum(sweep_ms) / max(len(sweep_ms), 1)
     achieved = table_bytes / (sweep_avg_ms * 1e-3) / 1e9 if sweep_ms else None
-    traffic = None
+    traffic, issue_pct = None, None
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "sweep_traffic.json")))
-        if t.get("n_elem") == N * K:
+        issue_pct = t.get("epoch_issue_active_pct")
+        if t.get("n_elem") == n_rows * K:
             traffic = t.get("epoch_dram_bytes_per_launch")
     except Exception:
         pass
@@ -373,6 +374,10 @@ def main_b200(args):
                          "algorithmic_bytes_per_launch": table_bytes, "avg_launch_ms": sweep_avg_ms,
                          "launches_timed": len(sweep_ms), "peak_source": peak_src,
                          "kernel_share_of_step": (sum(sweep_ms) / ms_total if sweep_ms else None),
+                         # the same work in the every-step formulation (EPOCH passes of 24 B/element): what HBM
+                         # would have to deliver to match this launch -- context, not the roofline fraction
+                         "per_step_formulation_equiv_GBps": (EPOCH * achieved if achieved else None),
+                         "issue_active_pct_ncu": issue_pct,
                          "note": "by design NOT HBM-bound: the kernel replays 16 optimizer steps per element in "
                                  "registers (IEEE div+sqrt recurrence, 29.5 instr/element/step against an arithmetic "
                                  "floor of 24) to cut HBM traffic 16x; its limiter is instruction issue (77 % "
