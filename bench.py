@@ -305,7 +305,13 @@ def main_b200(args):
         if model.epoch_pos == 0 and not sharded:                          # L2 terms of the epoch just closed
             reg_h.copy_(model.epoch_reg_terms(), non_blocking=True)
 
+    sampler2 = ClockSampler(local)
+    model.updater.sweep_events = []
+    sampler2.start()
     ms_e2e = timed(step_host, args.steps, 2, finish=model.flush)
+    sampler2.stop_flag = True
+    e2e_sweep_ms = [a.elapsed_time(b) for a, b in model.updater.sweep_events]
+    model.updater.sweep_events = None
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in pinned[0])
     last_loss = float(loss_h[(args.steps + 1) % loss_h.shape[0]][0] + reg_h[:, -1].sum())
@@ -366,7 +372,9 @@ def main_b200(args):
                                        f"dp{world}: replicated tables, all-gather of sparse gradients, all-reduce of "
                                        "dense gradients")},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12 + 8, "last_loss": last_loss},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12 + 8, "last_loss": last_loss,
+                    "sweep_avg_ms": (sum(e2e_sweep_ms) / len(e2e_sweep_ms) if e2e_sweep_ms else None),
+                    "clocks": sampler2.summary()},
             "gpu_launches": launches, "clocks": sampler.summary(),
             "roofline": {"kernel": f"epoch_sweep_kernel<ADAM> on fm_v ({EPOCH} Adam steps per element per pass)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
