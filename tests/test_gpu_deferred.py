@@ -76,3 +76,27 @@ def test_deferred_large_rows_k16_and_k256():
             ids, vals, labels = synth.criteo_batch(64, 2000, 39, seed=step, device="cuda")
             a.train_step(ids, vals, labels); b.train_step(ids, vals, labels)
         _same(a, b, f"K={K}")
+
+
+def test_deferred_bit_identical_on_zero_denormal_and_tiny_state():
+    """Rows nothing gathers are pulled to 0 by l2 + Adam and their m underflows: the sweep's grouped fast path has a
+    zero-group shortcut, a guarded range down to 2^-100 and the compiler's slow path below it.  All three must leave
+    the same bits as the every-step sweep."""
+    from tf_repos_b200 import synth
+    P = 3
+    a, b = _models("Adam", 1e-4, P, N=4096)
+    N, K = a.N, a.K
+    g = torch.Generator().manual_seed(11)
+    scales = torch.tensor([0.0, 1e-42, 1e-39, 1e-36, 1e-33, 1e-30, 1e-26, 1e-20, 1e-12, 1e-6, 1e-2, 1.0])
+    v = torch.randn(N, K, generator=g) * scales[torch.randint(0, len(scales), (N, 1), generator=g)]
+    v[::7] = torch.randn(N, K, generator=g)[::7] * scales[torch.randint(0, len(scales), (N, K), generator=g)][::7]  # mixed groups
+    w = torch.randn(N, generator=g) * scales[torch.randint(0, len(scales), (N,), generator=g)]
+    for m in (a, b):
+        m.load_variables({"fm_v": v, "fm_w": w})
+        # slots in every regime too: zero, denormal and tiny first moments; second moments from 0 upwards
+        m.fm_v.slots[0].copy_((torch.randn(N, K, generator=torch.Generator().manual_seed(5)) * 1e-38).cuda() * (torch.arange(N).cuda() % 3 == 0).float().view(N, 1))
+        m.fm_v.slots[1].copy_((torch.rand(N, K, generator=torch.Generator().manual_seed(6)) * 1e-30).cuda() * (torch.arange(N).cuda() % 2 == 0).float().view(N, 1))
+    for step in range(2 * P + 2):
+        ids, vals, labels = synth.criteo_batch(a.B, N, 39, seed=70 + step, device="cuda")
+        a.train_step(ids, vals, labels); b.train_step(ids, vals, labels)
+        _same(a, b, f"extreme state after step {step}")

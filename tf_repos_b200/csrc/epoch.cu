@@ -467,13 +467,17 @@ __global__ void __launch_bounds__(256) selftest_divsqrt_kernel(uint64_t seed, in
   unsigned long long bad_s = 0, bad_d = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t r0 = mix64(seed + 3 * (uint64_t)i), r1 = mix64(seed + 3 * (uint64_t)i + 1), r2 = mix64(seed + 3 * (uint64_t)i + 2);
-    const float v = test_float(r0, -101, 99);
+    const float v = test_float(r0, -101, 39);
     if (__float_as_uint(sqrt_rn_inrange(v)) != __float_as_uint(__fsqrt_rn(v))) ++bad_s;
-    float a = test_float(r1, -60, 59), b = test_float(r2, -60, 59);
+    // numerators over the whole guarded range [2^-100, 2^60) (half of them in the low decades), denominators over
+    // [2^-51, 2^21) and, for a quarter of the cases, of the Adam shape sqrt(v) + eps
+    float a = (r1 & 1) ? test_float(r1 >> 1, -100, -56) : test_float(r1 >> 1, -100, 59);
+    float b = test_float(r2, -51, 20);
     if (r1 >> 63) a = -a;
-    if ((r2 >> 62) & 1) b = __fadd_rn(__fsqrt_rn(v < 1e30f ? v : 1.f), 1e-8f);   // the Adam denominator shape
-    if (fabsf(b) < DIV_LO || fabsf(b) > DIV_HI) b = 1.f;
+    if (((r2 >> 61) & 3) == 0) b = __fadd_rn(__fsqrt_rn(v), 1e-8f);
     if (__float_as_uint(div_rn_inrange(a, b)) != __float_as_uint(__fdiv_rn(a, b))) ++bad_d;
+    // a zero numerator: the fast path must give a zero (either sign: see adam_untouched)
+    if (div_rn_inrange((r0 >> 62) & 1 ? -0.f : 0.f, b) != 0.f) ++bad_d;
   }
   if (bad_s) atomicAdd(&mism[0], bad_s);
   if (bad_d) atomicAdd(&mism[1], bad_d);
