@@ -390,7 +390,10 @@ def main_b200(args):
                                  "registers (IEEE div+sqrt recurrence, 29.5 instr/element/step against an arithmetic "
                                  "floor of 24) to cut HBM traffic 16x; its limiter is instruction issue (77 % "
                                  "issue-active, profiles/r01_ncu_epoch_sweep_full.txt).  The HBM-bound formulation "
-                                 "of the same update is reported under exact_every_step."}}
+                                 "of the same update is reported under exact_every_step.  The grouped IEEE fast path is valid "
+                                 "while |lr_t*m| >= 2^-100, i.e. for about the first 650 steps of a run with these "
+                                 "defaults (the timed steps are inside that window); later steps fall back to the "
+                                 "compiler's per-element div/sqrt (sweep ~1.3x slower), see DESIGN.md section 6."}}
     if exact_sweep_ms:
         ex_avg = sum(exact_sweep_ms) / len(exact_sweep_ms)
         tr = None
