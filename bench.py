@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=CFG["batch_size"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the lazy/infer side measurements")
+    ap.add_argument("--zipf", type=float, default=0.0,
+                    help="0 = uniform ids inside each categorical sub-vocabulary (default: the roofline-honest worst "
+                         "case); > 0 = heavy-tailed ids (synth.criteo_batch), the secondary distribution of SURVEY 8d")
     ap.add_argument("--tables", default="auto", choices=["auto", "replicated", "sharded"],
                     help="N>1: 'sharded' = rows owned by id %% N, NCCL all-to-all exchange (default); "
                          "'replicated' = data parallel with all-gathered sparse gradients")
@@ -162,6 +165,15 @@ def run_cpu(steps: int, warmup: int, budget_s: float, N: int, B: int):
     return B * done / dt, dt / done * 1e3, done, cores, desc
 
 
+def _tf_importable() -> bool:
+    """probe at run time; a TensorFlow that could run the reference has never been seen in this image."""
+    import importlib.util
+    try:
+        return importlib.util.find_spec("tensorflow") is not None
+    except Exception:
+        return False
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -172,7 +184,8 @@ def main_reference(args):
             "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: DeepFM 39 fields, 200M vocab, k=16, bs=8192 (exact TF semantics)",
-                       "note": "TensorFlow 1.4 / Python 2 reference cannot be installed here; oracle port timed"},
+                       "note": "TensorFlow 1.4 / Python 2 reference cannot be installed here; oracle port timed",
+                       "tensorflow_importable": _tf_importable()},
             "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -215,7 +228,7 @@ def main_b200(args):
         model = DeepFM(F, N, K, B, deep_layers=c["deep_layers"], dropout=c["dropout"], l2_reg=c["l2_reg"],
                        learning_rate=c["learning_rate"], optimizer=c["optimizer"], update_mode="exact_deferred",
                        epoch_steps=EPOCH, device=dev, seed=0, world=world)
-    host = [synth.criteo_batch(B, N, F, seed=rank * 1000 + i) for i in range(N_BATCHES)]
+    host = [synth.criteo_batch(B, N, F, seed=rank * 1000 + i, zipf=args.zipf) for i in range(N_BATCHES)]
     devb = [tuple(t.to(dev) for t in b) for b in host]
     pinned = [tuple(t.pin_memory() for t in b) for b in host]
     torch.cuda.synchronize()
@@ -364,7 +377,7 @@ def main_b200(args):
                                    "dropout 0.5, exact TensorFlow update semantics (every row moves every step); "
                                    f"exact-deferred update, epoch of {EPOCH} steps (state bit-identical to sweeping "
                                    "every step); the timed region ends with a flush of all deferred work",
-                       "vocab": N, "batch_per_gpu": B, "l2_flush": "inputs larger than L2: every epoch streams the "
+                       "vocab": N, "batch_per_gpu": B, "id_distribution": ("uniform" if args.zipf == 0.0 else f"heavy-tailed (zipf={args.zipf})"), "l2_flush": "inputs larger than L2: every epoch streams the "
                        "whole 38.4 GB fm_v/m/v state; 16 distinct pre-staged batches are cycled",
                        "parallelism": ("single GPU" if world == 1 else
                                        f"dp{world} batches, tables row-sharded by id % {world}: NCCL all-to-all of ids / "

@@ -29,6 +29,15 @@ for threads in (10, os.cpu_count() or 1):
     dt = time.perf_counter() - t0
     res[f"host_{threads}_threads"] = {"lines_per_s": LINES / dt, "GB_per_s": n_bytes / dt / 1e9}
 
+# the oracle's pure-Python decode_libsvm (what a Python-level restatement of the TF string ops costs), 5 000 lines
+from oracle import libsvm as olib  # noqa: E402
+sample = data.decode().splitlines()[:5000]
+t0 = time.perf_counter()
+for ln in sample:
+    olib.decode_libsvm(ln)
+dt = time.perf_counter() - t0
+res["oracle_python_1_thread"] = {"lines_per_s": len(sample) / dt, "GB_per_s": sum(len(l) + 1 for l in sample) / dt / 1e9}
+
 dev = torch.device("cuda:0")
 pinned = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).pin_memory()
 text = pinned.to(dev)
