@@ -3,7 +3,7 @@ B200 engine: same task types (train / eval / infer / export), same file globbing
 te*libsvm), same `model_dir + dt_dir` quirk (Q2), `pred.txt` with "%f\\n" per row, AUC with
 tf.metrics.auc's 200 thresholds, `global_step/sec` logging every log_steps, resume from the checkpoint
 in model_dir.  The tf.estimator runtime itself (hooks, summaries, TF_CONFIG parameter servers) is out of
-scope; --dist_mode != 0 is rejected with a pointer to torchrun."""
+scope; --dist_mode != 0 is rejected with a pointer to the multi-GPU engine classes."""
 from __future__ import annotations
 
 import glob
@@ -85,7 +85,8 @@ def run(build_model: Callable[[], object], model_name: str):
             print(k + " ", getattr(FLAGS, k))
     if FLAGS.dist_mode != 0:
         raise SystemExit("dist_mode=%d: the TF_CONFIG parameter-server modes (DeepFM.py:237-282) are replaced by "
-                         "synchronous data parallelism: launch with torchrun --nproc-per-node N" % FLAGS.dist_mode)
+                         "synchronous multi-GPU training (tf_repos_b200.sharded.ShardedDeepFM / DeepFM(world=N) under torchrun, "
+                         "see bench.py and DESIGN.md 7); this script drives one GPU" % FLAGS.dist_mode)
     if FLAGS._items().get("batch_norm"):
         raise SystemExit("--batch_norm: tf.contrib.layers.batch_norm is restated in oracle/ but not yet on the CUDA path")
     # ------init Envs------

@@ -110,7 +110,7 @@ def run():
         print(k + " ", getattr(FLAGS, k))
     if FLAGS.dist_mode:
         raise SystemExit("dist_mode: the TF_CONFIG parameter-server mode (wide_n_deep.py:153-178) is not provided; "
-                         "the other models scale with torchrun (DESIGN.md 7)")
+                         "multi-GPU training exists for DeepFM only (DESIGN.md 7)")
     tr_files = glob.glob("%s/tr*csv" % FLAGS.data_dir)
     random.shuffle(tr_files)
     print("tr_files:", tr_files)
