@@ -9,7 +9,7 @@ LIB       := tf_repos_b200/libctr_b200.so
 
 all: $(LIB)
 
-build/%.o: $(SRC_DIR)/%.cu $(SRC_DIR)/common.cuh include/ctr_b200.h
+build/%.o: $(SRC_DIR)/%.cu $(wildcard $(SRC_DIR)/*.cuh) include/ctr_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 

@@ -175,10 +175,17 @@ int ctr_epoch_tick(float* state, float* hyper, int n_hyper, float* lr_table, int
 int ctr_epoch_rows(int opt, int apply, float* var, float* slot0, float* slot1, uint8_t* last,
                    const int32_t* uniq, const int32_t* n_uniq, const float* g_uniq, int64_t n_max, int K,
                    const float* hyper, const float* lr_table, int j, double* ss, ctr_stream_t stream);
-/* ss_partials: device double[ctr_epoch_max_steps()][*n_partials_host] */
+/* All rows -> state after `upto` steps of this epoch.  Rows whose `last` byte equals `from` (nothing gathered
+ * them since the previous sweep; from = 0 after an epoch-end sweep) replay steps from..upto-1; the others replay
+ * last..upto-1.  reset != 0: epoch end, every `last` byte returns to 0; reset == 0: mid-epoch flush, `last` = upto.
+ * ss_partials: device double[ctr_epoch_max_steps()][*n_partials_host].
+ * list / list_cap / list_count / ss_rows (optional, Adam): scratch for the packed-pipe sweep (csrc/epoch_adam.cu):
+ * device int32[list_cap] with list_cap >= min(n_rows, ids gathered since `from`), a device int32 counter, and the
+ * row kernels' per-step sum(var^2) accumulator (the `ss` of ctr_epoch_rows).  NULL selects the scalar kernels. */
 int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* last, int64_t n_rows, int K,
-                    const float* hyper, const float* lr_table, int upto, int reset, double* ss_partials,
-                    int* n_partials_host, ctr_stream_t stream);
+                    const float* hyper, const float* lr_table, int from, int upto, int reset, double* ss_partials,
+                    int* n_partials_host, int32_t* list, int64_t list_cap, int32_t* list_count, double* ss_rows,
+                    ctr_stream_t stream);
 /* reg[s] (+)= scale*(ss_rows[s] + sum_b ss_partials[s][b]) for s < upto; clears ss_rows[s] */
 int ctr_epoch_reg_loss(double* ss_rows, const double* ss_partials, int n_partials, int upto, float scale,
                        float* reg, int accumulate, ctr_stream_t stream);
@@ -187,6 +194,12 @@ int ctr_epoch_reg_loss(double* ss_rows, const double* ss_partials, int n_partial
  * sqrt.rn / div.rn on n pseudo-random in-range operands (seeded; uniform mantissas, hard mantissa
  * patterns mixed in).  mismatches: device int64[2] = {sqrt mismatches, div mismatches} (overwritten). */
 int ctr_selftest_divsqrt(uint64_t seed, int64_t n, int64_t* mismatches, ctr_stream_t stream);
+/* The packed (FMUL2/FADD2/FFMA2) untouched-row Adam loops of the epoch sweep (csrc/adam_packed.cuh) against the
+ * scalar step, bit for bit, on n random 8-element states of a regime (0: normal range; 1: tiny / denormal / zero
+ * first moments; 2: also denormal / zero second moments), `steps` (1..4) steps each.
+ * out3: device int64[3] = {elements whose (var, m, v) bits differ, trajectories the validity check rejected, total}. */
+int ctr_selftest_adam_packed(int regime, uint64_t seed, int64_t n, int steps, float lr, float l2, int64_t* out3,
+                             ctr_stream_t stream);
 
 /* ---- loss head -----------------------------------------------------------------------------------
  * y = ((bias + y_a) + y_b) + y_c (NULL terms skipped; DeepFM.py:172-175), pred = sigmoid(y)

@@ -49,10 +49,11 @@ SIGNATURES = {
     "ctr_epoch_max_steps": (c_int, []),
     "ctr_epoch_tick": (c_int, [P, P, c_int, P, c_int, c_int, P]),
     "ctr_epoch_rows": (c_int, [c_int, c_int, P, P, P, P, P, P, P, c_int64, c_int, P, P, c_int, P, P]),
-    "ctr_epoch_sweep": (c_int, [c_int, P, P, P, P, c_int64, c_int, P, P, c_int, c_int, P,
-                                ctypes.POINTER(c_int), P]),
+    "ctr_epoch_sweep": (c_int, [c_int, P, P, P, P, c_int64, c_int, P, P, c_int, c_int, c_int, P,
+                                ctypes.POINTER(c_int), P, c_int64, P, P, P]),
     "ctr_epoch_reg_loss": (c_int, [P, P, c_int, c_int, c_float, P, c_int, P]),
     "ctr_selftest_divsqrt": (c_int, [c_uint64, c_int64, P, P]),
+    "ctr_selftest_adam_packed": (c_int, [c_int, c_uint64, c_int64, c_int, c_float, c_float, P, P]),
     "ctr_reduce_sum": (c_int, [P, c_int64, c_float, P, P, c_size_t, P]),
     "ctr_l2_loss_workspace_bytes": (c_size_t, [c_int64]),
     "ctr_l2_loss": (c_int, [P, c_int64, c_float, P, P, c_size_t, P]),

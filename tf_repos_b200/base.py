@@ -96,7 +96,7 @@ class CTRModel:
     # ---- deferred-mode plumbing ----------------------------------------------------------------------------
     def flush(self):
         """exact_deferred: bring every row to the current step (no-op otherwise)."""
-        if self.update_mode == "exact_deferred" and self.epoch_pos > 0:
+        if self.update_mode == "exact_deferred" and self.epoch_pos > self.updater.flush_pos:
             self.updater.epoch_sweep(self.tables, self.epoch_pos, reset=False, l2_reg=self.l2_reg)
 
     def set_update_mode(self, mode: str):

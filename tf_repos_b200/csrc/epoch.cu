@@ -23,6 +23,12 @@ namespace ctr {
 
 constexpr int EPOCH_MAX = 32;  // max steps per epoch (lr table / ss table size)
 
+// epoch_adam.cu: Adam sweep on the packed fp32 pipe (rows nothing gathered since `from`; the others go to `list`)
+bool launch_epoch_sweep_adam(float* var, float* slot0, float* slot1, const uint8_t* last, int64_t n_rows, int K,
+                             const float* hyper, const float* lr_table, int from, int upto, double* ss_partials,
+                             int n_partials, int32_t* list, int32_t* list_count, int64_t list_cap, int grid,
+                             cudaStream_t st);
+
 __device__ __forceinline__ float sq4(const float4& x) {
   return (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
 }
@@ -36,7 +42,7 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
                   uint8_t* __restrict__ last, const int32_t* __restrict__ uniq,
                   const int32_t* __restrict__ n_uniq, const float* __restrict__ g_uniq, int64_t n_max,
                   const float* __restrict__ hyper, const float* __restrict__ lr_table, int j,
-                  double* __restrict__ ss) {
+                  double* __restrict__ ss, int set_last) {
   constexpr int K = 4 * LPR * VEC;
   constexpr bool two = OptTraits<OPT>::slots == 2;
   __shared__ float ss_blk[EPOCH_MAX];  // <= 256 rows' worth per CTA: fp32 is plenty; global sums are double
@@ -95,6 +101,7 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
     if (lane == 0 && q != 0.f) atomicAdd(&ss_blk[j], q);
   }
   const bool wrote = active && (APPLY || l0 < j);
+  const uint8_t new_last = (uint8_t)(set_last >= 0 ? set_last : (APPLY ? j + 1 : j));
   if (wrote) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -105,7 +112,7 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
     }
   }
   __syncthreads();  // every lane of a row has read `last` before lane 0 of the row rewrites it
-  if (wrote && c == 0) last[id] = (uint8_t)(APPLY ? j + 1 : j);
+  if (active && c == 0 && (wrote || set_last >= 0)) last[id] = new_last;
   if (threadIdx.x < EPOCH_MAX && ss_blk[threadIdx.x] != 0.f) atomicAdd(&ss[threadIdx.x], (double)ss_blk[threadIdx.x]);
 }
 
@@ -116,7 +123,7 @@ epoch_rows_generic_kernel(float* __restrict__ var, float* __restrict__ slot0, fl
                           uint8_t* __restrict__ last, const int32_t* __restrict__ uniq,
                           const int32_t* __restrict__ n_uniq, const float* __restrict__ g_uniq,
                           int64_t n_max, int K, const float* __restrict__ hyper,
-                          const float* __restrict__ lr_table, int j, double* __restrict__ ss) {
+                          const float* __restrict__ lr_table, int j, double* __restrict__ ss, int set_last) {
   constexpr bool two = OptTraits<OPT>::slots == 2;
   __shared__ float ss_blk[EPOCH_MAX];
   if (threadIdx.x < EPOCH_MAX) ss_blk[threadIdx.x] = 0.f;
@@ -157,10 +164,10 @@ epoch_rows_generic_kernel(float* __restrict__ var, float* __restrict__ slot0, fl
     var[e] = x; slot0[e] = a;
     if (two) slot1[e] = b;
   }
-  // the row's `last` byte is written after every k of the row has read it; the host wrapper only
-  // admits K that divide 256 here, so a row never straddles two CTAs
+  // the row's `last` byte is written after every k of the row has read it; the launch uses (256/K)*K threads
+  // per CTA, so a row never straddles two CTAs
   __syncthreads();
-  if (active && k == 0) last[id] = (uint8_t)(APPLY ? j + 1 : j);
+  if (active && k == 0) last[id] = (uint8_t)(set_last >= 0 ? set_last : (APPLY ? j + 1 : j));
   if (threadIdx.x < EPOCH_MAX && ss_blk[threadIdx.x] != 0.f) atomicAdd(&ss[threadIdx.x], (double)ss_blk[threadIdx.x]);
 }
 
@@ -518,32 +525,24 @@ int ctr_epoch_tick(float* state, float* hyper, int n_hyper, float* lr_table, int
   return CTR_OK;
 }
 
-int ctr_epoch_rows(int opt, int apply, float* var, float* slot0, float* slot1, uint8_t* last,
-                   const int32_t* uniq, const int32_t* n_uniq, const float* g_uniq, int64_t n_max, int K,
-                   const float* hyper, const float* lr_table, int j, double* ss, ctr_stream_t stream) {
-  CTR_REQUIRE(n_max >= 0 && K > 0 && j >= 0 && j < EPOCH_MAX, CTR_ERR_INVALID_ARG,
-              "ctr_epoch_rows: bad n_max/K/j");
-  if (n_max == 0) return CTR_OK;
-  CTR_REQUIRE(var && slot0 && last && uniq && n_uniq && hyper && lr_table && ss, CTR_ERR_INVALID_ARG,
-              "ctr_epoch_rows: null buffer");
-  CTR_REQUIRE(!apply || g_uniq, CTR_ERR_INVALID_ARG, "ctr_epoch_rows: g_uniq required when apply != 0");
-  CTR_REQUIRE(n_slots_of(opt) == 1 || slot1, CTR_ERR_INVALID_ARG, "ctr_epoch_rows: slot1 required");
-  // generic path: a row's K threads must sit in one CTA (they synchronise on the row's `last` byte)
-  CTR_REQUIRE(K % 4 == 0 || 256 % K == 0, CTR_ERR_UNSUPPORTED,
-              "ctr_epoch_rows: K=%d must be a multiple of 4 or divide 256", K);
-  cudaStream_t st = as_stream(stream);
+static int launch_epoch_rows(int opt, int apply, float* var, float* slot0, float* slot1, uint8_t* last,
+                             const int32_t* uniq, const int32_t* n_uniq, const float* g_uniq, int64_t n_max, int K,
+                             const float* hyper, const float* lr_table, int j, double* ss, int set_last,
+                             cudaStream_t st) {
+  // generic path: a row's K threads sit in one CTA (they synchronise on the row's `last` byte)
+  const int gen_block = K <= 256 ? (256 / K) * K : 0;
 #define ER_K(OPT, AP, KK, LPR, VEC)                                                                  \
   case KK:                                                                                           \
     epoch_rows_kernel<OPT, LPR, VEC, AP><<<(unsigned)ceil_div64(n_max * LPR, 256), 256, 0, st>>>(    \
-        var, slot0, slot1, last, uniq, n_uniq, g_uniq, n_max, hyper, lr_table, j, ss);               \
+        var, slot0, slot1, last, uniq, n_uniq, g_uniq, n_max, hyper, lr_table, j, ss, set_last);     \
     break;
 #define ER_AP(OPT, AP)                                                                               \
   switch (K) {                                                                                       \
     ER_K(OPT, AP, 4, 1, 1) ER_K(OPT, AP, 8, 2, 1) ER_K(OPT, AP, 16, 4, 1) ER_K(OPT, AP, 32, 8, 1)    \
     ER_K(OPT, AP, 64, 16, 1) ER_K(OPT, AP, 128, 32, 1) ER_K(OPT, AP, 256, 32, 2)                     \
     default:                                                                                         \
-      epoch_rows_generic_kernel<OPT, AP><<<(unsigned)ceil_div64(n_max * K, 256), 256, 0, st>>>(      \
-          var, slot0, slot1, last, uniq, n_uniq, g_uniq, n_max, K, hyper, lr_table, j, ss);          \
+      epoch_rows_generic_kernel<OPT, AP><<<(unsigned)ceil_div64(n_max * K, gen_block), gen_block, 0, st>>>( \
+          var, slot0, slot1, last, uniq, n_uniq, g_uniq, n_max, K, hyper, lr_table, j, ss, set_last); \
   }
 #define ER_CALL(OPT)                     \
   if (apply) { ER_AP(OPT, true) } else { ER_AP(OPT, false) }
@@ -555,17 +554,40 @@ int ctr_epoch_rows(int opt, int apply, float* var, float* slot0, float* slot1, u
   return CTR_OK;
 }
 
+static bool epoch_rows_supported(int K) {
+  return K == 4 || K == 8 || K == 16 || K == 32 || K == 64 || K == 128 || K == 256 || (K >= 1 && K <= 256);
+}
+
+int ctr_epoch_rows(int opt, int apply, float* var, float* slot0, float* slot1, uint8_t* last,
+                   const int32_t* uniq, const int32_t* n_uniq, const float* g_uniq, int64_t n_max, int K,
+                   const float* hyper, const float* lr_table, int j, double* ss, ctr_stream_t stream) {
+  CTR_REQUIRE(n_max >= 0 && K > 0 && j >= 0 && j < EPOCH_MAX, CTR_ERR_INVALID_ARG,
+              "ctr_epoch_rows: bad n_max/K/j");
+  if (n_max == 0) return CTR_OK;
+  CTR_REQUIRE(var && slot0 && last && uniq && n_uniq && hyper && lr_table && ss, CTR_ERR_INVALID_ARG,
+              "ctr_epoch_rows: null buffer");
+  CTR_REQUIRE(!apply || g_uniq, CTR_ERR_INVALID_ARG, "ctr_epoch_rows: g_uniq required when apply != 0");
+  CTR_REQUIRE(n_slots_of(opt) == 1 || slot1, CTR_ERR_INVALID_ARG, "ctr_epoch_rows: slot1 required");
+  CTR_REQUIRE(epoch_rows_supported(K), CTR_ERR_UNSUPPORTED, "ctr_epoch_rows: K=%d must be <= 256", K);
+  return launch_epoch_rows(opt, apply, var, slot0, slot1, last, uniq, n_uniq, g_uniq, n_max, K, hyper, lr_table, j,
+                           ss, -1, as_stream(stream));
+}
+
 int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* last, int64_t n_rows, int K,
-                    const float* hyper, const float* lr_table, int upto, int reset, double* ss_partials,
-                    int* n_partials_host, ctr_stream_t stream) {
-  CTR_REQUIRE(n_rows >= 0 && K > 0 && upto >= 0 && upto <= EPOCH_MAX, CTR_ERR_INVALID_ARG,
-              "ctr_epoch_sweep: bad n_rows/K/upto");
-  // tuning hook (tools/tune_epoch.py): CTR_EPOCH_CFG selects (unroll, CTAs/SM) of the K%4==0 kernel
-  static int cfg = -1;
+                    const float* hyper, const float* lr_table, int from, int upto, int reset, double* ss_partials,
+                    int* n_partials_host, int32_t* list, int64_t list_cap, int32_t* list_count, double* ss_rows,
+                    ctr_stream_t stream) {
+  CTR_REQUIRE(n_rows >= 0 && K > 0 && from >= 0 && from <= upto && upto <= EPOCH_MAX, CTR_ERR_INVALID_ARG,
+              "ctr_epoch_sweep: bad n_rows/K/from/upto");
+  // tuning hook (tools/tune_epoch.py): CTR_EPOCH_CFG selects (unroll, CTAs/SM) of the scalar K%4==0 kernel;
+  // CTR_EPOCH_SCALAR=1 routes Adam through the scalar kernels as well (A/B against the packed sweep)
+  static int cfg = -1, force_scalar = 0;
   if (cfg < 0) {
     const char* e = getenv("CTR_EPOCH_CFG");
-    cfg = e ? atoi(e) : 4;  // (unroll 2, 3 CTAs/SM) measured fastest on B200 with ~1.6 % gathered rows: profiles/
+    cfg = e ? atoi(e) : 4;
     if (cfg < 0 || cfg > 7) cfg = 4;
+    const char* f = getenv("CTR_EPOCH_SCALAR");
+    force_scalar = f ? atoi(f) : 0;
   }
   static const int kBlocksPerSm[8] = {3, 4, 2, 6, 3, 2, 6, 4};
   const int grid = sm_count() * 3;
@@ -578,7 +600,30 @@ int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* la
   CTR_REQUIRE(n_slots_of(opt) == 1 || slot1, CTR_ERR_INVALID_ARG, "ctr_epoch_sweep: slot1 required");
   cudaStream_t st = as_stream(stream);
   const int64_t n_elem = n_rows * K;
-  if (K % 4 == 0) {
+  const int f4 = K / 4;
+  const bool row_in_warp = K % 4 == 0 && (f4 & (f4 - 1)) == 0 && f4 <= 32;
+
+  // ---- Adam on the packed pipe (epoch_adam.cu): untouched rows here, gathered rows through `list` ----------
+  if (opt == CTR_OPT_ADAM && !force_scalar && list && list_count && ss_rows && list_cap > 0 && from < upto &&
+      epoch_rows_supported(K) && (K % 4 == 0 || (K == 1 && n_rows % 4 == 0 && ((uintptr_t)last & 3) == 0))) {
+    CTR_REQUIRE(cudaMemsetAsync(list_count, 0, sizeof(int32_t), st) == cudaSuccess, CTR_ERR_CUDA,
+                "ctr_epoch_sweep: memset failed");
+    const bool ok = launch_epoch_sweep_adam(var, slot0, slot1, last, n_rows, K, hyper, lr_table, from, upto,
+                                            ss_partials, n_partials, list, list_count, list_cap, grid, st);
+    CTR_REQUIRE(ok, CTR_ERR_UNSUPPORTED, "ctr_epoch_sweep: packed path refused K=%d", K);
+    CTR_LAUNCHED("ctr_epoch_sweep(adam)");
+    // rows gathered since `from`: catch up from their own `last` to upto; they get their final `last` here
+    const int rc = launch_epoch_rows(opt, 0, var, slot0, slot1, last, list, list_count, nullptr, list_cap, K, hyper,
+                                     lr_table, upto, ss_rows, reset ? 0 : upto, st);
+    if (rc != CTR_OK) return rc;
+    if (!(reset && from == 0)) {   // untouched rows hold `from`: rewrite (an epoch-end sweep leaves their 0 alone)
+      epoch_last_kernel<<<grid, 256, 0, st>>>(last, n_rows, upto, reset);
+      CTR_LAUNCHED("ctr_epoch_sweep(last)");
+    }
+    return CTR_OK;
+  }
+
+  if (row_in_warp) {   // a row's float4s sit in one warp: `last` can be rewritten in place
 #define ES_LAUNCH(OPT, U, MB)                                                                         \
   epoch_sweep_kernel<OPT, U, MB><<<grid_v, 256, 0, st>>>(var, slot0, slot1, last, n_elem / 4, K, hyper, \
                                                          lr_table, upto, reset, ss_partials, n_partials)
@@ -605,6 +650,8 @@ int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* la
 #undef ES1_CALL
     CTR_LAUNCHED("ctr_epoch_sweep(k1)");
   } else {
+    // rows that span warps / CTAs (K/4 not a power of two <= 32) or K % 4 != 0: one thread per element, `last`
+    // rewritten by a separate pass once every element of the row has read it
 #define ESG_CALL(OPT)                                                                                \
   epoch_sweep_generic_kernel<OPT><<<grid, 256, 0, st>>>(var, slot0, slot1, last, n_elem, K, hyper,   \
                                                         lr_table, upto, reset, ss_partials, n_partials);

@@ -130,10 +130,15 @@ class SparseUpdater:
         assert 1 <= P <= pmax
         dev = tables[0].var.device
         self.P = P
+        self.flush_pos = 0   # steps of the current epoch every row's stored state already contains (mid-epoch flush)
         self.n_epart = ops.epoch_partials_count()
         self.ep = {}
         for t in tables:
+            # rows gathered since the last sweep, collected by the packed Adam sweep for its second pass
+            cap = max(min(self.n * pmax, t.N), 1)
             self.ep[t.name] = dict(
+                list=torch.empty(cap, dtype=torch.int32, device=dev),
+                list_count=torch.zeros(1, dtype=torch.int32, device=dev),
                 last=torch.zeros(t.N, dtype=torch.uint8, device=dev),
                 ss=torch.zeros(pmax, dtype=torch.float64, device=dev),
                 partials=torch.zeros(pmax * self.n_epart, dtype=torch.float64, device=dev),
@@ -164,12 +169,14 @@ class SparseUpdater:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
             ops.epoch_sweep(o.opt, t.var, t.slot(0), t.slot(1), e["last"], t.N, t.K, o.record(HYPER_TABLE),
-                            o.lr_table, upto, reset, e["partials"])
+                            o.lr_table, self.flush_pos, upto, reset, e["partials"], e["list"], e["list_count"],
+                            e["ss"])
             if ev is not None:
                 ev[1].record()
                 self.sweep_events.append(ev)
             # accumulate: a mid-epoch flush and the epoch-end sweep each contribute their share
             ops.epoch_reg_loss(e["ss"], e["partials"], self.n_epart, upto, 0.5 * l2_reg, e["reg"], accumulate=True)
+        self.flush_pos = 0 if reset else upto
 
     def epoch_begin(self):
         for e in self.ep.values():

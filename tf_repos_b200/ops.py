@@ -371,14 +371,18 @@ def epoch_partials_count() -> int:
     return int(_L.ctr_device_sm_count()) * 6
 
 
-def epoch_sweep(opt, var, slot0, slot1, last, n_rows, K, hyper, lr_table, upto: int, reset: bool, ss_partials):
+def epoch_sweep(opt, var, slot0, slot1, last, n_rows, K, hyper, lr_table, from_: int, upto: int, reset: bool,
+                ss_partials, list_buf=None, list_count=None, ss_rows=None):
+    """list_buf / list_count / ss_rows: scratch of the packed-pipe Adam sweep (None: scalar kernels)."""
     n_part = ctypes.c_int(0)
     check(
         _L.ctr_epoch_sweep(
             opt, _p(var, torch.float32, "var"), _p(slot0, torch.float32, "slot0"),
             _p(slot1, torch.float32, "slot1"), _p(last, torch.uint8, "last"), n_rows, K,
-            _p(hyper, torch.float32, "hyper"), _p(lr_table, torch.float32, "lr_table"), upto, int(reset),
-            _p(ss_partials, torch.float64, "ss_partials"), ctypes.byref(n_part), _stream()),
+            _p(hyper, torch.float32, "hyper"), _p(lr_table, torch.float32, "lr_table"), from_, upto, int(reset),
+            _p(ss_partials, torch.float64, "ss_partials"), ctypes.byref(n_part),
+            _p(list_buf, torch.int32, "list"), (list_buf.numel() if list_buf is not None else 0),
+            _p(list_count, torch.int32, "list_count"), _p(ss_rows, torch.float64, "ss_rows"), _stream()),
         "ctr_epoch_sweep")
     return n_part.value
 
@@ -389,6 +393,14 @@ def epoch_reg_loss(ss_rows, ss_partials, n_partials, upto, scale, reg, accumulat
                               n_partials, upto, float(scale), _p(reg, torch.float32, "reg"), int(accumulate),
                               _stream()),
         "ctr_epoch_reg_loss")
+
+
+def selftest_adam_packed(regime: int, seed: int, n: int, steps: int, lr: float, l2: float, device) -> tuple:
+    """(elements with differing bits, rejected trajectories, total) of the packed Adam loops vs the scalar step"""
+    out = torch.zeros(3, dtype=torch.int64, device=device)
+    check(_L.ctr_selftest_adam_packed(int(regime), int(seed), int(n), int(steps), float(lr), float(l2),
+                                      _p(out, torch.int64, "out3"), _stream()), "ctr_selftest_adam_packed")
+    return tuple(out.tolist())
 
 
 def selftest_divsqrt(seed: int, n: int, device) -> tuple:

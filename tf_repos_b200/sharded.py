@@ -95,7 +95,7 @@ class ShardedDeepFM:
             dist.all_to_all_single(out, inp, out_splits, in_splits, group=self.group)
 
     def flush(self):
-        if self.update_mode == "exact_deferred" and self.epoch_pos > 0:
+        if self.update_mode == "exact_deferred" and self.epoch_pos > self.updater.flush_pos:
             self.updater.epoch_sweep(self.tables, self.epoch_pos, reset=False, l2_reg=self.l2_reg)
 
     def load_global_tables(self, fm_v: torch.Tensor, fm_w: torch.Tensor):
