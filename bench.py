@@ -117,6 +117,32 @@ def cpu_vocab(N: int) -> int:
     return n
 
 
+def _synth_module():
+    """tf_repos_b200/synth.py (pure numpy/torch batch generator) loaded BY PATH: importing the package would dlopen
+    libctr_b200.so, and the reference arm must not map any product code."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ctr_synth_standalone", os.path.join(ROOT, "tf_repos_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _interleave_host_memory():
+    """set_mempolicy(MPOL_INTERLEAVE, all nodes): the oracle's table-sized arrays are first-touched by one thread and
+    would otherwise sit on one NUMA node (the CPU arm moved 4x between boxes in round 1).  Best effort."""
+    try:
+        import ctypes
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if len(nodes) < 2:
+            return f"{len(nodes)} NUMA node(s)"
+        mask = ctypes.c_ulong(sum(1 << int(d[4:]) for d in nodes))
+        libc = ctypes.CDLL(None, use_errno=True)
+        rc = libc.syscall(238, 3, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))   # x86_64 set_mempolicy
+        return f"{len(nodes)} NUMA nodes, interleave rc={rc}"
+    except Exception as e:  # pragma: no cover
+        return f"interleave unavailable ({e})"
+
+
 def run_cpu(steps: int, warmup: int, budget_s: float, N: int, B: int):
     """Times oracle.DeepFM.train_step (TF-exact semantics, all host threads).  Returns
     (samples_per_s, ms_per_step, steps_timed, cores, sample description)."""
@@ -124,8 +150,9 @@ def run_cpu(steps: int, warmup: int, budget_s: float, N: int, B: int):
 
     from oracle import models as om
     from oracle import tf_semantics as tfs
-    from tf_repos_b200 import synth
+    synth = _synth_module()
 
+    numa = _interleave_host_memory()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     tfs.FAST_SQRT = True  # multithreaded (non-IEEE) sqrt: fastest honest CPU number
@@ -160,7 +187,7 @@ def run_cpu(steps: int, warmup: int, budget_s: float, N: int, B: int):
             break
     dt = time.perf_counter() - t0
     desc = (f"{done} exact-TF train steps of oracle.DeepFM (PyTorch-CPU fp32 restatement of DeepFM.py model_fn), "
-            f"B={B}, F=39, k=16, vocab {n_cpu}" + ("" if n_cpu == N else f" (cut from {N} to fit host RAM; the "
+            f"B={B}, F=39, k=16, vocab {n_cpu}, {warmup} warm-up steps, {numa}" + ("" if n_cpu == N else f" (cut from {N} to fit host RAM; the "
             f"dense-sweep cost scales with vocab, so this FLATTERS the CPU)"))
     return B * done / dt, dt / done * 1e3, done, cores, desc
 
@@ -178,10 +205,12 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # one warm-up step and a wall-clock budget: a full-vocabulary CPU step takes seconds to tens of seconds
-    sps, ms, done, cores, desc = run_cpu(args.steps, min(args.warmup, 1), 150.0, args.vocab, args.batch)
+    # three warm-up steps (first touches of the table-sized scratch arrays) and a wall-clock budget: a
+    # full-vocabulary CPU step takes seconds
+    wu = max(min(args.warmup, 3), 1)
+    sps, ms, done, cores, desc = run_cpu(args.steps, wu, 150.0, args.vocab, args.batch)
     line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
-            "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": done, "warmup": wu, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: DeepFM 39 fields, 200M vocab, k=16, bs=8192 (exact TF semantics)",
                        "note": "TensorFlow 1.4 / Python 2 reference cannot be installed here; oracle port timed",
@@ -255,6 +284,7 @@ def main_b200(args):
         barrier()
         if model.updater.sweep_events is not None:
             model.updater.sweep_events = []
+            model.updater.sweep_steps = []
         counts["n0"] = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -278,6 +308,7 @@ def main_b200(args):
     sampler.stop_flag = True
     launches = counts["launches"]
     sweep_ms = [a.elapsed_time(b) for a, b in model.updater.sweep_events]
+    sweep_steps = list(model.updater.sweep_steps)
     model.updater.sweep_events = None
     model.check_ids()
     ms_step = ms_total / args.steps
@@ -331,7 +362,91 @@ def main_b200(args):
 
     extras = {}
     exact_sweep_ms = []
+
+    def sweep_stats(ms_list, steps_list):
+        full = [m for m, st in zip(ms_list, steps_list) if st == EPOCH]
+        part = [(m, st) for m, st in zip(ms_list, steps_list) if st != EPOCH]
+        return full, part
+
     if not args.no_extras and not sharded:
+        # ---- heavy-tailed ids (SURVEY 8d secondary distribution) ------------------------------------------------
+        if args.zipf == 0.0:
+            zb = [tuple(t.to(dev) for t in synth.criteo_batch(B, N, F, seed=7000 + i, zipf=1.05)) for i in range(N_BATCHES)]
+
+            def step_zipf(i):
+                model.train_step(*zb[i % N_BATCHES])
+            ms_z = timed(step_zipf, 2 * EPOCH, 3, finish=model.flush)
+            extras["zipf_1.05"] = {"value": world * B * 2 * EPOCH / (ms_z * 1e-3), "unit": "samples/s",
+                                   "ms_per_step": ms_z / (2 * EPOCH),
+                                   "note": "same workload, heavy-tailed ids inside each categorical sub-vocabulary"}
+            del zb
+
+        # ---- e2e from libsvm TEXT: host bytes -> H2D -> device tokenizer (csrc/libsvm_device.cu) -> step ---------
+        import io
+        from tf_repos_b200 import ops as _ops
+        texts = []
+        for b in host[:4]:
+            buf = io.StringIO()
+            ids_n, vals_n, lab_n = (t.numpy() for t in b)
+            for r in range(B):
+                buf.write("%d " % int(lab_n[r]))
+                buf.write(" ".join("%d:%s" % (int(i), ("%.6f" % v) if v != 1.0 else "1") for i, v in zip(ids_n[r], vals_n[r])))
+                buf.write("\n")
+            raw = buf.getvalue().encode()
+            texts.append(torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory())
+        text_dev = [torch.empty(max(t.numel() for t in texts), dtype=torch.uint8, device=dev) for _ in range(2)]
+        loss_t = torch.zeros(3).pin_memory()
+
+        def step_text(i):
+            src = texts[i % len(texts)]
+            dst = text_dev[i % 2][: src.numel()]
+            dst.copy_(src, non_blocking=True)
+            ids_t, vals_t, labels_t, consumed, needs_host = _ops.parse_libsvm_device(dst, F, B, final_chunk=True)
+            assert not needs_host and ids_t.shape[0] == B
+            parts = model.train_step(ids_t, vals_t, labels_t)
+            loss_t.copy_(parts, non_blocking=True)
+        ms_t = timed(step_text, 2 * EPOCH, 3, finish=model.flush)
+        extras["e2e_text"] = {"value": world * B * 2 * EPOCH / (ms_t * 1e-3), "unit": "samples/s",
+                              "ms_per_step": ms_t / (2 * EPOCH), "h2d_bytes_per_step": int(texts[0].numel()),
+                              "note": "libsvm text in pinned host memory -> H2D -> device tokenizer (decode_libsvm, "
+                                      "DeepFM.py:65-81) -> train step, loss read back; one host sync per step (row count)"}
+        del texts, text_dev
+
+        # ---- steady state: the tables as they look after a long run -------------------------------------------
+        # l2 + Adam pull every row nothing gathers to ~FLT_MIN with a denormal first moment (DESIGN.md section 6;
+        # tests/test_fastpath_guard_coverage.py simulates it).  The packed sweep handles that state with its scaled
+        # loops; this leg times the same steps from that state.
+        model.set_update_mode("exact_deferred")          # closes the open epoch
+        g = torch.Generator(device=dev).manual_seed(11)
+        CH = 1 << 27
+        for t in model.tables:
+            flat = [t.var.view(-1), t.slots[0].view(-1), t.slots[1].view(-1)]
+            for o in range(0, flat[0].numel(), CH):
+                n = min(CH, flat[0].numel() - o)
+                u = lambda: torch.rand(n, device=dev, generator=g)
+                sgn = lambda: torch.where(u() < 0.5, -1.0, 1.0)
+                flat[0][o:o + n] = sgn() * (0.25 + 4.0 * u()) * 2.0 ** -126
+                mm = sgn() * u() * 4e-42
+                flat[1][o:o + n] = torch.where(u() < 0.2, torch.zeros_like(mm), mm)
+                flat[2][o:o + n] = (0.5 + u()) * 1e-24
+        model.opt.state[0] = 0.0
+        model.opt.state[1] = 0.999 ** 3000
+        model.updater.sweep_events = []
+        ms_ss = timed(step_dev, 2 * EPOCH, 3, finish=model.flush)
+        ss_full, _ = sweep_stats([a.elapsed_time(b) for a, b in model.updater.sweep_events], model.updater.sweep_steps)
+        model.updater.sweep_events = None
+        extras["steady_state"] = {"value": world * B * 2 * EPOCH / (ms_ss * 1e-3), "unit": "samples/s",
+                                  "ms_per_step": ms_ss / (2 * EPOCH),
+                                  "sweep_full_pass_ms": (sum(ss_full) / len(ss_full) if ss_full else None),
+                                  "note": "same steps from the parked long-run state (var ~FLT_MIN, denormal m, "
+                                          "v ~1e-24, lr_t ~ lr)"}
+        # back to a fresh table for the side measurements below
+        model.set_update_mode("exact_deferred")
+        for t in model.tables:
+            _ops.init_trunc_normal(t.var, (2.0 / (t.N + t.K)) ** 0.5 if t.K > 1 else (1.0 / t.N) ** 0.5, 3)
+            for sl in t.slots:
+                _ops.fill(sl, 0.0)
+
         model.set_update_mode("exact")
         model.updater.sweep_events = []
         ms_ex = timed(step_dev, max(args.steps // 2, 4), 2)
@@ -360,8 +475,9 @@ def main_b200(args):
     peak, peak_src = peaks()
     n_rows = model.N_local if sharded else N
     table_bytes = n_rows * K * 4 * 6  # Adam: read var,m,v + write var,m,v (24 B/element) per pass over the table
-    sweep_avg_ms = sum(sweep_ms) / max(len(sweep_ms), 1)
-    achieved = table_bytes / (sweep_avg_ms * 1e-3) / 1e9 if sweep_ms else None
+    full_ms, part = sweep_stats(sweep_ms, sweep_steps)
+    sweep_avg_ms = sum(full_ms) / max(len(full_ms), 1)
+    achieved = table_bytes / (sweep_avg_ms * 1e-3) / 1e9 if full_ms else None
     traffic, issue_pct = None, None
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "sweep_traffic.json")))
@@ -393,7 +509,10 @@ def main_b200(args):
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak if achieved else None), "traffic": traffic,
                          "algorithmic_bytes_per_launch": table_bytes, "avg_launch_ms": sweep_avg_ms,
-                         "launches_timed": len(sweep_ms), "peak_source": peak_src,
+                         "launches_timed": len(full_ms), "peak_source": peak_src,
+                         # passes that replayed fewer steps (the flush that ends the timed region): same bytes, less
+                         # arithmetic -- reported apart, NOT averaged into `achieved`
+                         "partial_passes": [{"steps": st, "ms": m, "GBps": table_bytes / (m * 1e-3) / 1e9} for m, st in part],
                          "kernel_share_of_step": (sum(sweep_ms) / ms_total if sweep_ms else None),
                          # the same work in the every-step formulation (EPOCH passes of 24 B/element): what HBM
                          # would have to deliver to match this launch -- context, not the roofline fraction

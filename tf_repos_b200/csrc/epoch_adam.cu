@@ -17,6 +17,8 @@
 //
 // Bound: 2 MUFU per element-step at 16 MUFU lanes/clk/SM => 22.8 ms per 16-step pass over 3.2e9 elements
 // at 1.9 GHz; HBM traffic stays 24 B/element per pass (11.7 ms at the measured peak).
+#include <stdlib.h>
+
 #include "adam_packed.cuh"
 
 namespace ctr {
@@ -427,35 +429,53 @@ __global__ void __launch_bounds__(256) selftest_adam_packed_kernel(uint64_t seed
 }
 
 // launcher used by ctr_epoch_sweep (epoch.cu).  Returns false if this path does not apply.
-static int g_sweep_smem_set = 0;
+// CTR_SWEEP_MINB (tuning hook, tools/time_sweep.py): resident CTAs per SM the kernel is compiled for (2, 3, 4)
+template <int MINB>
+static void launch_sweep_minb(float* var, float* slot0, float* slot1, const uint8_t* last, int64_t n_rows, int K,
+                              const float* hyper, const float* lr_table, int from, int upto, double* ss_partials,
+                              int n_partials, int32_t* list, int32_t* list_count, int64_t list_cap, cudaStream_t st) {
+  static bool attr = false;
+  const int nsteps = upto - from;
+  const size_t smem = (EPOCH_MAX_A + 2 * (size_t)nsteps * SWEEP_THREADS) * sizeof(float);
+  if (!attr) {
+    const int mx = (EPOCH_MAX_A + 2 * EPOCH_MAX_A * SWEEP_THREADS) * (int)sizeof(float);
+    cudaFuncSetAttribute(epoch_sweep_adam_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(epoch_sweep_adam_k1_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    attr = true;
+  }
+  const float nz = -0.0f;
+  const int grid = sm_count() * MINB;
+  if (K % 4 == 0) {
+    const int f4 = K / 4;
+    const int sh = (f4 & (f4 - 1)) == 0 ? (31 - __builtin_clz((unsigned)f4)) : -1;
+    epoch_sweep_adam_kernel<MINB><<<grid, SWEEP_THREADS, smem, st>>>(var, slot0, slot1, last, n_rows * f4, f4, sh, hyper,
+                                                                     lr_table, from, upto, ss_partials, n_partials, list,
+                                                                     list_count, list_cap, nz);
+  } else {
+    epoch_sweep_adam_k1_kernel<MINB><<<grid, SWEEP_THREADS, smem, st>>>(var, slot0, slot1, last, n_rows / 4, hyper,
+                                                                        lr_table, from, upto, ss_partials, n_partials,
+                                                                        list, list_count, list_cap, nz);
+  }
+}
+
 bool launch_epoch_sweep_adam(float* var, float* slot0, float* slot1, const uint8_t* last, int64_t n_rows, int K,
                              const float* hyper, const float* lr_table, int from, int upto, double* ss_partials,
                              int n_partials, int32_t* list, int32_t* list_count, int64_t list_cap, int grid,
                              cudaStream_t st) {
-  const int nsteps = upto - from;
-  const size_t smem = (EPOCH_MAX_A + 2 * (size_t)nsteps * SWEEP_THREADS) * sizeof(float);
-  if (!g_sweep_smem_set) {
-    const int mx = (EPOCH_MAX_A + 2 * EPOCH_MAX_A * SWEEP_THREADS) * (int)sizeof(float);
-    cudaFuncSetAttribute(epoch_sweep_adam_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(epoch_sweep_adam_k1_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    g_sweep_smem_set = 1;
+  (void)grid;
+  if (!(K % 4 == 0 || (K == 1 && n_rows % 4 == 0 && ((uintptr_t)last & 3) == 0))) return false;
+  static int minb = 0;
+  if (!minb) {
+    const char* e = getenv("CTR_SWEEP_MINB");
+    minb = e ? atoi(e) : 3;
+    if (minb < 2 || minb > 4) minb = 3;
   }
-  const float nz = -0.0f;
-  if (K % 4 == 0) {
-    const int f4 = K / 4;
-    const int sh = (f4 & (f4 - 1)) == 0 ? (31 - __builtin_clz((unsigned)f4)) : -1;
-    epoch_sweep_adam_kernel<3><<<grid, SWEEP_THREADS, smem, st>>>(var, slot0, slot1, last, n_rows * f4, f4, sh, hyper,
-                                                                  lr_table, from, upto, ss_partials, n_partials, list,
-                                                                  list_count, list_cap, nz);
-    return true;
-  }
-  if (K == 1 && n_rows % 4 == 0 && ((uintptr_t)last & 3) == 0) {
-    epoch_sweep_adam_k1_kernel<3><<<grid, SWEEP_THREADS, smem, st>>>(var, slot0, slot1, last, n_rows / 4, hyper,
-                                                                     lr_table, from, upto, ss_partials, n_partials,
-                                                                     list, list_count, list_cap, nz);
-    return true;
-  }
-  return false;
+#define SW_ARGS var, slot0, slot1, last, n_rows, K, hyper, lr_table, from, upto, ss_partials, n_partials, list, list_count, list_cap, st
+  if (minb == 2) launch_sweep_minb<2>(SW_ARGS);
+  else if (minb == 4) launch_sweep_minb<4>(SW_ARGS);
+  else launch_sweep_minb<3>(SW_ARGS);
+#undef SW_ARGS
+  return true;
 }
 
 }  // namespace ctr

@@ -118,6 +118,7 @@ class SparseUpdater:
         # [l2*l2_loss(V), l2*l2_loss(W)] of the PRE-step tables (what `loss` of this step contains)
         self.reg = torch.zeros(2, **f32)
         self.sweep_events = None  # set to [] to collect (start, end) CUDA events around the V sweep
+        self.sweep_steps = []     # parallel to sweep_events: steps replayed by each pass (deferred mode)
 
     def dedup(self, ids_flat: torch.Tensor, g_rows: torch.Tensor, g_w: Optional[torch.Tensor]):
         ops.unique_segment(ids_flat, self.uw)
@@ -174,6 +175,7 @@ class SparseUpdater:
             if ev is not None:
                 ev[1].record()
                 self.sweep_events.append(ev)
+                self.sweep_steps.append(upto - self.flush_pos)   # optimizer steps this pass replayed per element
             # accumulate: a mid-epoch flush and the epoch-end sweep each contribute their share
             ops.epoch_reg_loss(e["ss"], e["partials"], self.n_epart, upto, 0.5 * l2_reg, e["reg"], accumulate=True)
         self.flush_pos = 0 if reset else upto

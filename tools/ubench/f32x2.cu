@@ -4,8 +4,9 @@
 #include <cuda_runtime.h>
 template <int MODE> __global__ void __launch_bounds__(256) k(float* out, int iters, float a, float b) {
   float2 x[8];
+  unsigned y[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f - i);
+  for (int i = 0; i < 8; ++i) { x[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f - i); y[i] = threadIdx.x + i; }
   const float2 A = make_float2(a, a), B = make_float2(b, b);
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -14,12 +15,16 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, int ite
       if (MODE == 1) { x[i] = __ffma2_rn(x[i], A, B); }                                            // 1 FFMA2
       if (MODE == 2) { asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x[i].x)); asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x[i].y)); }  // 2 MUFU
       if (MODE == 3) { x[i] = __ffma2_rn(x[i], A, B); asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x[i].x)); }  // mix: 1 FFMA2 + 1 MUFU
-      if (MODE == 4) { x[i] = __fmul2_rn(x[i], A); x[i] = __fadd2_rn(x[i], B); }                   // FMUL2 + FADD2 (may be contracted)
+      if (MODE == 4) { x[i] = __fmul2_rn(x[i], A); x[i] = __fadd2_rn(x[i], B); }                   // FMUL2 + FADD2: ptxas contracts them to ONE FFMA2
+      if (MODE == 5) { x[i] = __ffma2_rn(x[i], A, B); y[i] = (y[i] ^ (y[i] << 1)) + 0x9e3779b9u; }   // FFMA2 + 2 independent ALU ops (LOP3/IADD)
+      if (MODE == 6) { x[i].x = fminf(fminf(x[i].x, a), x[i].y); x[i].y = fmaxf(x[i].y, b); }       // FMNMX3 + FMNMX
+      if (MODE == 7) { x[i] = __fmul2_rn(x[i], A); }                                               // FMUL2 alone
+      if (MODE == 8) { x[i] = __fadd2_rn(x[i], B); }                                               // FADD2 alone
     }
   }
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s += x[i].x + x[i].y;
+  for (int i = 0; i < 8; ++i) s += x[i].x + x[i].y + (MODE == 5 ? (float)y[i] : 0.f);
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 template <int MODE> void run(const char* name, double inst_per_iter_thread) {
@@ -41,6 +46,10 @@ int main() {
   run<1>("FFMA2 x8 per iter (packed)", 8);
   run<2>("MUFU.RSQ x16 per iter", 16);
   run<3>("FFMA2 x8 + MUFU x8 per iter", 16);
-  run<4>("FMUL2+FADD2 x8 per iter", 16);
+  run<4>("FMUL2+FADD2 x8 per iter (contracted by ptxas: 8 FFMA2)", 8);
+  run<5>("FFMA2 x8 + ALU x16 per iter", 24);
+  run<6>("FMNMX3 x8 + FMNMX x8 per iter", 16);
+  run<7>("FMUL2 x8 per iter", 8);
+  run<8>("FADD2 x8 per iter", 8);
   return 0;
 }
