@@ -18,7 +18,8 @@ def main():
     run(lambda: DCN(FLAGS.field_size, FLAGS.feature_size, FLAGS.embedding_size, FLAGS.batch_size,
                     deep_layers=FLAGS.deep_layers, cross_layers=FLAGS.cross_layers, dropout=FLAGS.dropout,
                     l2_reg=FLAGS.l2_reg, learning_rate=FLAGS.learning_rate, optimizer=FLAGS.optimizer,
-                    update_mode=FLAGS.update_mode), "DCN")
+                    update_mode=FLAGS.update_mode,
+                 batch_norm=FLAGS.batch_norm, batch_norm_decay=FLAGS.batch_norm_decay), "DCN")
 
 
 if __name__ == "__main__":

@@ -243,6 +243,20 @@ int ctr_fc1_bwd(const float* in_a, int Ka, const float* in_b, int Kb, const floa
 int ctr_dropout_mask(float* mask, int64_t n, float keep_prob, uint64_t seed, const float* step_dev,
                      ctr_stream_t stream);
 
+/* ---- batch normalisation after the relu of a hidden layer ------------------------------------------
+ * Replaces batch_norm_layer (DeepFM.py:159-160,231-235; DCN.py:171,241-247; PNN.py:181; NFM.py:143; DIN.py:206):
+ * tf.contrib.layers.batch_norm(decay, center=True, scale=True, updates_collections=None), epsilon 0.001 [TF-sem],
+ * followed by the layer's dropout (drop_mask NULL = none).  x, out: [n, H] row-major.
+ * train != 0: batch moments (biased variance) -> save_mean / save_var [H]; moving_mean / moving_var are updated in
+ * place (moving -= (moving - batch)*(1 - decay)).  train == 0: moving statistics, no dropout, nothing written but out.
+ * ctr_bn_bwd: gradients through the batch moments; d_x [n,H], d_gamma / d_beta [H] (overwritten). */
+int ctr_bn_fwd(const float* x, int n, int H, const float* gamma, const float* beta, float* moving_mean,
+               float* moving_var, int train, float decay, float eps, const float* drop_mask, float keep_prob, float* out,
+               float* save_mean, float* save_var, ctr_stream_t stream);
+int ctr_bn_bwd(const float* d_out, const float* x, int n, int H, const float* save_mean, const float* save_var,
+               const float* gamma, float eps, const float* drop_mask, float keep_prob, float* d_x, float* d_gamma,
+               float* d_beta, ctr_stream_t stream);
+
 /* ---- K5: DCN cross network (DCN.py:140-145) ------------------------------------------------------
  * x_{l+1} = x0 * (x_l . w_l) + x_l + b_l,  l = 0..L-1;  w,b: [L,D];  x0: [B,D], D = F*K (D%4==0, <=2048)
  * fwd saves the L scalars s[b,l] = x_l . w_l;  bwd recomputes x_l from x0 and s.

@@ -356,13 +356,15 @@ class _LinearEmb(OracleModel, MLPMixin):
 class NFM(_LinearEmb):
     """NFM.py:94-200."""
 
-    def __init__(self, field_size, feature_size, embedding_size, deep_layers="128,64", dropout="0.5,0.8,0.8", seed=0, **kw):
+    def __init__(self, field_size, feature_size, embedding_size, deep_layers="128,64", dropout="0.5,0.8,0.8", seed=0,
+                 batch_norm=False, batch_norm_decay=0.9, **kw):
         kw.setdefault("l2_reg", 0.001); kw.setdefault("learning_rate", 0.05)
         super().__init__(**kw)
         self.layers, self.keep = _ints(deep_layers), _floats(dropout)
+        self.batch_norm, self.bn_decay = batch_norm, batch_norm_decay           # NFM.py:142-143
         gen = torch.Generator().manual_seed(seed)
         self._base(field_size, feature_size, embedding_size, gen)
-        self.build_mlp(self.K, self.layers, gen)
+        self.build_mlp(self.K, self.layers, gen, batch_norm=batch_norm)
         self.init_slots()
 
     def forward(self, rows, dense, batch, train, masks=None):
@@ -370,7 +372,8 @@ class NFM(_LinearEmb):
         x = 0.5 * (emb.sum(1) ** 2 - (emb ** 2).sum(1))                                   # NFM.py:126-128
         if train:
             x = tfs.dropout(x, self.keep[0], None if masks is None else masks.get("bi"))  # :136-137
-        h = self.run_mlp(x, dense, self.layers, self.keep, train, None if masks is None else masks.get("mlp"))
+        h = self.run_mlp(x, dense, self.layers, self.keep, train, None if masks is None else masks.get("mlp"),
+                         batch_norm=self.batch_norm, bn_decay=self.bn_decay)
         y_d = tfs.fully_connected(h, dense["Deep-part/deep_out/weights"], dense["Deep-part/deep_out/biases"], None).reshape(-1)
         y = dense["bias"] * torch.ones_like(y_d) + y_linear + y_d                          # :152-155
         return {"y": y}
@@ -380,15 +383,16 @@ class PNN(_LinearEmb):
     """PNN.py:102-238, model_type in {FNN, Inner, Outer}."""
 
     def __init__(self, field_size, feature_size, embedding_size, model_type="Inner", deep_layers="256,128,64",
-                 dropout="0.5,0.5,0.5", seed=0, **kw):
+                 dropout="0.5,0.5,0.5", seed=0, batch_norm=False, batch_norm_decay=0.9, **kw):
         super().__init__(**kw)
         self.model_type = model_type
+        self.batch_norm, self.bn_decay = batch_norm, batch_norm_decay           # PNN.py:180-181
         self.layers, self.keep = _ints(deep_layers), _floats(dropout)
         gen = torch.Generator().manual_seed(seed)
         self._base(field_size, feature_size, embedding_size, gen)
         P = field_size * (field_size - 1) // 2
         dz = field_size * embedding_size + {"FNN": 0, "Inner": P, "Outer": P * embedding_size ** 2}[model_type]
-        self.build_mlp(dz, self.layers, gen)
+        self.build_mlp(dz, self.layers, gen, batch_norm=batch_norm)
         self.init_slots()
 
     def forward(self, rows, dense, batch, train, masks=None):
@@ -407,7 +411,8 @@ class PNN(_LinearEmb):
                 z = torch.cat([x, (p * q).sum(-1)], 1)                                     # :152-153
             else:
                 z = torch.cat([x, torch.einsum("api,apj->apij", p, q).reshape(B, -1)], 1)  # :166-167
-        h = self.run_mlp(z, dense, self.layers, self.keep, train, None if masks is None else masks.get("mlp"))
+        h = self.run_mlp(z, dense, self.layers, self.keep, train, None if masks is None else masks.get("mlp"),
+                         batch_norm=self.batch_norm, bn_decay=self.bn_decay)
         y_d = tfs.fully_connected(h, dense["Deep-part/deep_out/weights"], dense["Deep-part/deep_out/biases"], None).reshape(-1)
         return {"y": dense["bias"] * torch.ones_like(y_d) + y_linear + y_d}                # :190-193
 

@@ -37,6 +37,7 @@ def floats(s) -> List[float]:
 
 
 class CTRModel:
+    batch_norm, bn_decay = False, 0.9   # --batch_norm / --batch_norm_decay (set by the sub-class before _build)
     table_name = "emb"          # TF variable name of the [N,K] table
     linear_name: Optional[str] = None  # TF variable name of the [N] first-order table, if any
 
@@ -121,6 +122,9 @@ class CTRModel:
         self.flush()
         out = {t.name: t.var for t in self.tables}
         out.update(self.dense.views)
+        mlp = getattr(self, "mlp", None)
+        if mlp is not None:
+            out.update(mlp.bn_state)      # non-trainable moving_mean / moving_variance (batch_norm=True)
         return out
 
     def load_variables(self, values: Dict[str, torch.Tensor]):

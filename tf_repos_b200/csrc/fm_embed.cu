@@ -15,6 +15,8 @@
 //   are issued before the first use.  ids/vals are read coalesced (one field per lane) and
 //   broadcast with shuffles; the first-order scalar gather is done one-field-per-lane as well
 //   (32 independent 4 B gathers in flight).  x is written as float4 (sample-contiguous, coalesced).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ctr {
@@ -104,6 +106,137 @@ fm_embed_fwd_kernel(const void* __restrict__ ids, const float* __restrict__ vals
   }
   // d = S*S - q, with S*S rounded first (as tf.square then tf.subtract do): a sample with a single
   // active field gives exactly 0, like the reference.
+  float4 d[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+    d[v] = make_float4(__fmul_rn(s[v].x, s[v].x) - q[v].x, __fmul_rn(s[v].y, s[v].y) - q[v].y,
+                       __fmul_rn(s[v].z, s[v].z) - q[v].z, __fmul_rn(s[v].w, s[v].w) - q[v].w);
+  if (mode == CTR_FM_NFM) {
+    if (slot == 0) {
+      float4* o = reinterpret_cast<float4*>(y2 + (int64_t)b * K) + c;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o[v * LPR] = f4_scale(d[v], 0.5f);
+    }
+  } else {
+    float t = 0.f;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) t += f4_hsum(d[v]);
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) t += __shfl_xor_sync(FULL_MASK, t, o);
+    if (lane == 0) y2[b] = 0.5f * t;
+  }
+}
+
+
+// ---- K1 with the rows staged in shared memory by the TMA engine (1-D bulk copies) -----------------------------
+// north_star: "TMA staging of embedding rows into shared memory".  Same mapping and the same arithmetic order as
+// fm_embed_fwd_kernel (=> bit-identical outputs); the only difference is how a row travels: one lane per field
+// issues cp.async.bulk global -> shared (K*4 bytes, completion counted on the warp's mbarrier) instead of K/4
+// lanes issuing 128-bit loads into registers.  Selected with CTR_FM_EMBED_TMA=1 (tools/bench_kernels.py measures
+// both; DESIGN.md records the result).  One warp per sample, F <= 64, K in {16, 32, 64, 128}.
+__device__ __forceinline__ uint32_t fe_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int LPR, int VEC, typename IdT>
+__global__ void __launch_bounds__(128)
+fm_embed_fwd_tma_kernel(const void* __restrict__ ids, const float* __restrict__ vals,
+                        const float* __restrict__ V, const float* __restrict__ W, int64_t N, int B,
+                        int F, int mode, float* __restrict__ x, float* __restrict__ y_w,
+                        float* __restrict__ y2, float* __restrict__ S, int32_t* __restrict__ oob) {
+  constexpr int K = 4 * LPR * VEC;
+  constexpr int RPW = 32 / LPR;
+  constexpr int ITERS = 32 / RPW;
+  constexpr int UNROLL = (ITERS <= 8) ? ITERS : 8;
+  extern __shared__ __align__(128) uint8_t fe_smem[];
+  __shared__ __align__(8) uint64_t bars[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+  float* rows = reinterpret_cast<float*>(fe_smem) + (size_t)warp * F * K;      // [F][K] of this warp's sample
+  const uint32_t bar = fe_smem_u32(&bars[warp]);
+  if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  if (b >= B) return;
+  const int slot = lane / LPR;
+  const int c = lane % LPR;
+  const int64_t base = (int64_t)b * F;
+  float yw = 0.f;
+  int64_t id_l[2] = {0, 0};
+  float val_l[2] = {0.f, 0.f};
+  if (lane == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(F * K * 4)) : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int fl = h * 32 + lane;
+    if (fl < F) {
+      int64_t id = load_id<IdT>(ids, base + fl);
+      float val = vals[base + fl];
+      if (id < 0 || id >= N) {
+        if (oob) { if (atomicAdd(&oob[0], 1) == 0) oob[1] = (int32_t)id; }
+        id = 0; val = 0.f;
+      }
+      id_l[h] = id; val_l[h] = val;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       fe_smem_u32(rows + (size_t)fl * K)),
+                   "l"(V + id * K), "r"((uint32_t)(K * 4)), "r"(bar)
+                   : "memory");
+      if (W) yw = fmaf(__ldg(W + id), val, yw);
+    }
+  }
+  {  // wait for all F rows of this sample
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "FE_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra FE_DONE;\n\t"
+        "bra FE_WAIT;\n\t"
+        "FE_DONE:\n\t"
+        "}" ::"r"(bar) : "memory");
+  }
+  float4 s[VEC], q[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { s[v] = f4_zero(); q[v] = f4_zero(); }
+  for (int fbase = 0, h = 0; fbase < F; fbase += 32, ++h) {
+    const int nf = min(32, F - fbase);
+#pragma unroll UNROLL
+    for (int it = 0; it < ITERS; ++it) {
+      const int fj = it * RPW + slot;
+      const float val = __shfl_sync(FULL_MASK, h == 0 ? val_l[0] : val_l[1], fj);
+      if (fj < nf) {
+        const float4* row = reinterpret_cast<const float4*>(rows + (size_t)(fbase + fj) * K) + c;
+        float4 e[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) e[v] = f4_scale(row[v * LPR], val);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          s[v] = f4_add(s[v], e[v]);
+          q[v] = f4_fma(e[v], e[v], q[v]);
+        }
+        if (x) {
+          float4* xr = reinterpret_cast<float4*>(x + (base + fbase + fj) * K) + c;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) xr[v * LPR] = e[v];
+        }
+      }
+    }
+  }
+  if (W && y_w) {
+    yw = warp_sum(yw);
+    if (lane == 0) y_w[b] = yw;
+  }
+  if (mode == CTR_FM_PLAIN) return;
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { s[v] = f4_add(s[v], f4_shfl_xor(s[v], o)); q[v] = f4_add(q[v], f4_shfl_xor(q[v], o)); }
+  }
+  if (S && slot == 0) {
+    float4* Sr = reinterpret_cast<float4*>(S + (int64_t)b * K) + c;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) Sr[v * LPR] = s[v];
+  }
   float4 d[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v)
@@ -267,6 +400,31 @@ static int launch_fwd(const void* ids, const float* vals, const float* V, const 
                       int32_t* oob, cudaStream_t st) {
   const int wpb = 4;
   dim3 grid((B + wpb - 1) / wpb), block(wpb * 32);
+  static int use_tma = -1;
+  if (use_tma < 0) { const char* e = getenv("CTR_FM_EMBED_TMA"); use_tma = e ? atoi(e) : 0; }
+  if (use_tma && F <= 64 && (K == 16 || K == 32 || K == 64 || K == 128)) {
+    const size_t smem = (size_t)wpb * F * K * 4;
+#define TMA_CASE(KK, LPR, VEC)                                                                             \
+  case KK: {                                                                                               \
+    static size_t set = 0;                                                                                 \
+    if (smem > set) {                                                                                      \
+      cudaFuncSetAttribute(fm_embed_fwd_tma_kernel<LPR, VEC, IdT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      set = smem;                                                                                          \
+    }                                                                                                      \
+    fm_embed_fwd_tma_kernel<LPR, VEC, IdT><<<grid, block, smem, st>>>(ids, vals, V, W, N, B, F, mode, x, y_w, y2, S, oob); \
+  } break;
+    if (smem <= 200 * 1024) {
+      switch (K) {
+        TMA_CASE(16, 4, 1)
+        TMA_CASE(32, 8, 1)
+        TMA_CASE(64, 16, 1)
+        TMA_CASE(128, 32, 1)
+      }
+#undef TMA_CASE
+      CTR_LAUNCHED("ctr_fm_embed_fwd(tma)");
+      return CTR_OK;
+    }
+  }
 #define FWD_CASE(KK, LPR, VEC)                                                                     \
   case KK:                                                                                         \
     fm_embed_fwd_kernel<LPR, VEC, IdT><<<grid, block, 0, st>>>(ids, vals, V, W, N, B, F, mode, x,  \

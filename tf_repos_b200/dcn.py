@@ -22,8 +22,10 @@ class DCN(CTRModel):
     def __init__(self, field_size: int, feature_size: int, embedding_size: int, batch_size: int,
                  deep_layers="256,128,64", cross_layers: int = 3, dropout="0.5,0.5,0.5", l2_reg: float = 1e-4,
                  learning_rate: float = 5e-4, optimizer: str = "Adam", update_mode: str = "exact",
-                 device="cuda", seed: int = 0, world: int = 1, epoch_steps: int = 8):
+                 device="cuda", seed: int = 0, world: int = 1, epoch_steps: int = 8, batch_norm: bool = False,
+                 batch_norm_decay: float = 0.9):
         self.layers, self.keep, self.L = ints(deep_layers), floats(dropout), int(cross_layers)
+        self.batch_norm, self.bn_decay = bool(batch_norm), float(batch_norm_decay)
         super().__init__(field_size, feature_size, embedding_size, batch_size, l2_reg, learning_rate, optimizer,
                          update_mode, device, seed, world, epoch_steps)
         self.emb = self.V
@@ -35,7 +37,7 @@ class DCN(CTRModel):
         f32 = dict(dtype=torch.float32, device=dev)
         # out_layer input = [x_L (D), x_deep (last hidden)]  (DCN.py:178-181)
         self.mlp = MLP(D, self.layers, self.keep, B, dev, scope="Deep-Network", out_scope="DCN-out/out_layer",
-                       out_extra_in=D, seed=self.seed)
+                       out_extra_in=D, seed=self.seed, batch_norm=self.batch_norm, bn_decay=self.bn_decay)
         specs = [("cross_b", (L, D)), ("cross_w", (L, D))] + self.mlp.specs()
         self.dense = DenseVars(specs, self.opt, dev, l2_names=("cross_b", "cross_w"))
         gen = torch.Generator().manual_seed(self.seed)

@@ -23,8 +23,10 @@ class DeepFM(CTRModel):
     def __init__(self, field_size: int, feature_size: int, embedding_size: int, batch_size: int,
                  deep_layers="256,128,64", dropout="0.5,0.5,0.5", l2_reg: float = 1e-4,
                  learning_rate: float = 5e-4, optimizer: str = "Adam", update_mode: str = "exact",
-                 device="cuda", seed: int = 0, world: int = 1, epoch_steps: int = 8):
+                 device="cuda", seed: int = 0, world: int = 1, epoch_steps: int = 8, batch_norm: bool = False,
+                 batch_norm_decay: float = 0.9):
         self.layers, self.keep = ints(deep_layers), floats(dropout)
+        self.batch_norm, self.bn_decay = bool(batch_norm), float(batch_norm_decay)
         super().__init__(field_size, feature_size, embedding_size, batch_size, l2_reg, learning_rate, optimizer,
                          update_mode, device, seed, world, epoch_steps)
         self.fm_v, self.fm_w = self.V, self.W
@@ -32,7 +34,8 @@ class DeepFM(CTRModel):
     def _build(self):
         B, F, K, dev = self.B, self.F, self.K, self.device
         f32 = dict(dtype=torch.float32, device=dev)
-        self.mlp = MLP(F * K, self.layers, self.keep, B, dev, seed=self.seed)
+        self.mlp = MLP(F * K, self.layers, self.keep, B, dev, seed=self.seed, batch_norm=self.batch_norm,
+                       bn_decay=self.bn_decay)
         self.dense = DenseVars([("fm_bias", (1,))] + self.mlp.specs(), self.opt, dev)
         self.mlp.init(self.dense, torch.Generator().manual_seed(self.seed))
         self.x = torch.empty(B, F * K, **f32)      # scaled embeddings = deep_inputs (DeepFM.py:151)

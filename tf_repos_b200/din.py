@@ -35,8 +35,12 @@ class DIN:
                  max_a_int: int = 8, deep_layers="256,128,64", dropout="0.5,0.5,0.5", attention_layers="256",
                  attention_pooling: bool = True, l2_reg: float = 1e-4, learning_rate: float = 5e-4,
                  optimizer: str = "Adam", update_mode: str = "exact", device="cuda", seed: int = 0,
-                 epoch_steps: int = 8):
+                 epoch_steps: int = 8, batch_norm: bool = False, batch_norm_decay: float = 0.9):
         assert update_mode in ("exact", "exact_deferred", "lazy")
+        if batch_norm and attention_pooling:
+            # DIN.py:166 calls batch_norm_layer(train_phase=train_phase) inside attention_unit, where train_phase is
+            # not defined (it is assigned later, DIN.py:189-193): the reference raises NameError (quirk Q5)
+            raise NameError("name 'train_phase' is not defined (DIN.py:166: --batch_norm with --attention_pooling)")
         if len(ints(attention_layers)) != 1:
             raise NotImplementedError("one attention hidden layer (the reference default '256')")
         self.Fp, self.N, self.K, self.B, self.P = field_size, feature_size, embedding_size, batch_size, max_len
@@ -54,7 +58,7 @@ class DIN:
         self.off_u = Fp * K
         self.off_a = Fp * K + 4 * K
         self.mlp = MLP(self.Dx, self.layers, self.keep, B, dev, scope="MLP-layer", out_scope="DIN-out/din_out",
-                       seed=seed)
+                       seed=seed, batch_norm=batch_norm, bn_decay=batch_norm_decay)
         specs = self.mlp.specs()
         if attention_pooling:
             specs = [(f"{ATT}/att_fc0/weights", (3 * K, H)), (f"{ATT}/att_fc0/biases", (H,)),
@@ -122,13 +126,14 @@ class DIN:
 
     # ---- plumbing -------------------------------------------------------------------------------------
     def flush(self):
-        if self.update_mode == "exact_deferred" and self.epoch_pos > 0:
+        if self.update_mode == "exact_deferred" and self.epoch_pos > self.updater.flush_pos:
             self.updater.epoch_sweep(self.tables, self.epoch_pos, reset=False, l2_reg=self.l2_reg)
 
     def variables(self) -> Dict[str, torch.Tensor]:
         self.flush()
         out = {"embeddings": self.V.var}
         out.update(self.dense.views)
+        out.update(self.mlp.bn_state)
         return out
 
     def load_variables(self, values: Dict[str, torch.Tensor]):

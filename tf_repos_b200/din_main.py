@@ -117,8 +117,6 @@ def run():
         print(k + " ", getattr(FLAGS, k))
     if FLAGS.dist_mode != 0:
         raise SystemExit("dist_mode=%d: the TF_CONFIG parameter-server modes are not provided (DESIGN.md 7)" % FLAGS.dist_mode)
-    if FLAGS.batch_norm:
-        raise SystemExit("--batch_norm: not on the CUDA path (and undefined inside attention_unit in the reference, quirk Q5)")
     tr_files = glob.glob("%s/tr/*tfrecord" % FLAGS.data_dir)
     random.shuffle(tr_files)
     print("tr_files:", tr_files)
@@ -144,7 +142,7 @@ def run():
     model = DIN(F, FLAGS.feature_size, FLAGS.embedding_size, B, P, max_a_int=A, deep_layers=FLAGS.deep_layers,
                 dropout=FLAGS.dropout, attention_layers=FLAGS.attention_layers, attention_pooling=FLAGS.attention_pooling,
                 l2_reg=FLAGS.l2_reg, learning_rate=FLAGS.learning_rate, optimizer=FLAGS.optimizer,
-                update_mode=FLAGS.update_mode)
+                update_mode=FLAGS.update_mode, batch_norm=FLAGS.batch_norm, batch_norm_decay=FLAGS.batch_norm_decay)
     restore_checkpoint(model, FLAGS.model_dir)
     dev = model.device
 

@@ -87,8 +87,6 @@ def run(build_model: Callable[[], object], model_name: str):
         raise SystemExit("dist_mode=%d: the TF_CONFIG parameter-server modes (DeepFM.py:237-282) are replaced by "
                          "synchronous multi-GPU training (tf_repos_b200.sharded.ShardedDeepFM / DeepFM(world=N) under torchrun, "
                          "see bench.py and DESIGN.md 7); this script drives one GPU" % FLAGS.dist_mode)
-    if FLAGS._items().get("batch_norm"):
-        raise SystemExit("--batch_norm: tf.contrib.layers.batch_norm is restated in oracle/ but not yet on the CUDA path")
     # ------init Envs------
     tr_files = glob.glob("%s/tr*libsvm" % FLAGS.data_dir)
     random.shuffle(tr_files)

@@ -3,7 +3,9 @@ layer, forward and backward, through libctr_b200.so (csrc/fc.cu).  No torch comp
 
 fp32 throughout (the logit parity target is 1e-5 relative, which rules out TF32/BF16 tensor-core
 inputs without split-precision emulation).  All buffers are allocated once (CUDA-graph capturable).
-batch_norm=True (tf.contrib.layers.batch_norm, DeepFM.py:231-235) is not on this path yet.
+batch_norm=True inserts batch_norm_layer (DeepFM.py:159-160,231-235) between a layer's relu and its dropout
+(csrc/batch_norm.cu): trainable `bn_{i}/gamma|beta` live with the other dense variables, the non-trainable
+`bn_{i}/moving_mean|moving_variance` in `bn_state` (saved with checkpoints / exports).
 """
 from __future__ import annotations
 
@@ -20,7 +22,8 @@ class MLP:
 
     def __init__(self, in_dim: int, layers: Sequence[int], keep_prob: Sequence[float], B: int, device,
                  scope: str = "Deep-part", out_scope: Optional[str] = "deep_out", out_extra_in: int = 0,
-                 seed: int = 0, layer_fmt: str = "mlp{i}", w_name: str = "weights", b_name: str = "biases"):
+                 seed: int = 0, layer_fmt: str = "mlp{i}", w_name: str = "weights", b_name: str = "biases",
+                 batch_norm: bool = False, bn_decay: float = 0.9):
         # layer_fmt / w_name / b_name: TF variable naming (contrib fully_connected: mlp{i}/weights|biases;
         # the canned estimators' Dense layers: hiddenlayer_{i}/kernel|bias)
         self.layer_fmt, self.w_name, self.b_name = layer_fmt, w_name, b_name
@@ -39,6 +42,16 @@ class MLP:
         self.y = torch.empty(B, **f32)
         self.dx = torch.empty(B, in_dim, **f32)
         self.d_extra = torch.empty(B, out_extra_in, **f32) if out_extra_in else None
+        self.batch_norm, self.bn_decay = bool(batch_norm), float(bn_decay)
+        self.bn_state = {}
+        if self.batch_norm:
+            self.r = [torch.empty(B, w, **f32) for w in self.layers]       # relu output = batch_norm input
+            self.dr = [torch.empty(B, w, **f32) for w in self.layers]
+            self.bn_mean = [torch.zeros(w, **f32) for w in self.layers]    # batch moments saved for the backward
+            self.bn_var = [torch.ones(w, **f32) for w in self.layers]
+            for i, w in enumerate(self.layers):
+                self.bn_state[f"{scope}/bn_{i}/moving_mean"] = torch.zeros(w, **f32)
+                self.bn_state[f"{scope}/bn_{i}/moving_variance"] = torch.ones(w, **f32)
         dims = [in_dim] + self.layers
         ws = max([ops.fc_bwd_workspace_bytes(B, dims[i], dims[i + 1]) for i in range(len(self.layers))] +
                  [ops.fc1_bwd_workspace_bytes(B, self.last_dim, out_extra_in), 16])
@@ -51,10 +64,15 @@ class MLP:
     def _b(self, i: int) -> str:
         return f"{self.scope}/{self.layer_fmt.format(i=i)}/{self.b_name}"
 
+    def _bn(self, i: int, what: str) -> str:
+        return f"{self.scope}/bn_{i}/{what}"
+
     def specs(self):
         out, d = [], self.in_dim
         for i, w in enumerate(self.layers):
             out += [(self._w(i), (d, w)), (self._b(i), (w,))]
+            if self.batch_norm:
+                out += [(self._bn(i, "gamma"), (w,)), (self._bn(i, "beta"), (w,))]
             d = w
         if self.out_scope:
             out += [(f"{self.out_name}/{self.w_name}", (self.out_in, 1)), (f"{self.out_name}/{self.b_name}", (1,))]
@@ -67,6 +85,8 @@ class MLP:
                 lim = (6.0 / (shape[0] + shape[1])) ** 0.5
                 w = (torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * lim
                 dv[name].copy_(w.to(torch.float32))
+            elif name.endswith("/gamma"):       # batch_norm: gamma ones, beta zeros (the flat buffer starts at zero)
+                dv[name].fill_(1.0)
 
     # ---- forward -------------------------------------------------------------------------------
     def forward_hidden(self, x: torch.Tensor, dv: DenseVars, train: bool, masks=None, step_dev=None) -> torch.Tensor:
@@ -84,7 +104,14 @@ class MLP:
                 ops.dropout_mask(m, self.keep[i], self.seed * 131 + i, step_dev)
             self._active[i] = m
             h = self.h[i][:n]
-            ops.fc_fwd(a, W, b, m, self.keep[i], 1, h)
+            if self.batch_norm:   # relu -> batch_norm -> dropout (DeepFM.py:156-162)
+                r = self.r[i][:n]
+                ops.fc_fwd(a, W, b, None, 1.0, 1, r)
+                ops.bn_fwd(r, dv[self._bn(i, "gamma")], dv[self._bn(i, "beta")], self.bn_state[self._bn(i, "moving_mean")],
+                           self.bn_state[self._bn(i, "moving_variance")], train, self.bn_decay, m, self.keep[i], h,
+                           self.bn_mean[i], self.bn_var[i])
+            else:
+                ops.fc_fwd(a, W, b, m, self.keep[i], 1, h)
             a = h
         return a
 
@@ -119,7 +146,13 @@ class MLP:
             W = dv[self._w(i)]
             a = self.h[i - 1][:n] if i > 0 else x
             d_in = self.dh[i - 1][:n] if i > 0 else (self.dx[:n] if need_dx else None)
-            ops.fc_bwd(a, W, self.h[i][:n], self._active[i], self.keep[i], d, 1, d_in,
-                       dv.grads[self._w(i)], dv.grads[self._b(i)], self.ws)
+            if self.batch_norm:
+                r, dr = self.r[i][:n], self.dr[i][:n]
+                ops.bn_bwd(d, r, self.bn_mean[i], self.bn_var[i], dv[self._bn(i, "gamma")], self._active[i], self.keep[i],
+                           dr, dv.grads[self._bn(i, "gamma")], dv.grads[self._bn(i, "beta")])
+                ops.fc_bwd(a, W, r, None, 1.0, dr, 1, d_in, dv.grads[self._w(i)], dv.grads[self._b(i)], self.ws)
+            else:
+                ops.fc_bwd(a, W, self.h[i][:n], self._active[i], self.keep[i], d, 1, d_in,
+                           dv.grads[self._w(i)], dv.grads[self._b(i)], self.ws)
             d = d_in
         return self.dx[:n] if need_dx else None

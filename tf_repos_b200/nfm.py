@@ -17,15 +17,16 @@ class NFM(CTRModel):
 
     def __init__(self, field_size, feature_size, embedding_size, batch_size, deep_layers="128,64",
                  dropout="0.5,0.8,0.8", l2_reg=0.001, learning_rate=0.05, optimizer="Adam", update_mode="exact",
-                 device="cuda", seed=0, world=1, epoch_steps=8):
+                 device="cuda", seed=0, world=1, epoch_steps=8, batch_norm=False, batch_norm_decay=0.9):
         self.layers, self.keep = ints(deep_layers), floats(dropout)
+        self.batch_norm, self.bn_decay = bool(batch_norm), float(batch_norm_decay)
         super().__init__(field_size, feature_size, embedding_size, batch_size, l2_reg, learning_rate, optimizer,
                          update_mode, device, seed, world, epoch_steps)
 
     def _build(self):
         B, F, K, dev = self.B, self.F, self.K, self.device
         f32 = dict(dtype=torch.float32, device=dev)
-        self.mlp = MLP(K, self.layers, self.keep, B, dev, seed=self.seed)
+        self.mlp = MLP(K, self.layers, self.keep, B, dev, seed=self.seed, batch_norm=self.batch_norm, bn_decay=self.bn_decay)
         self.dense = DenseVars([("bias", (1,))] + self.mlp.specs(), self.opt, dev)
         self.mlp.init(self.dense, torch.Generator().manual_seed(self.seed))
         self.x = torch.empty(B, F * K, **f32)

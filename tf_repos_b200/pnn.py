@@ -16,11 +16,12 @@ class PNN(CTRModel):
 
     def __init__(self, field_size, feature_size, embedding_size, batch_size, model_type="Inner",
                  deep_layers="256,128,64", dropout="0.5,0.5,0.5", l2_reg=1e-4, learning_rate=5e-4, optimizer="Adam",
-                 update_mode="exact", device="cuda", seed=0, world=1, epoch_steps=8):
+                 update_mode="exact", device="cuda", seed=0, world=1, epoch_steps=8, batch_norm=False, batch_norm_decay=0.9):
         if model_type not in ("FNN", "Inner", "Outer"):
             raise NameError(f"model_type {model_type!r}: deep_inputs is undefined (PNN.py:139-167)")
         self.model_type = model_type
         self.layers, self.keep = ints(deep_layers), floats(dropout)
+        self.batch_norm, self.bn_decay = bool(batch_norm), float(batch_norm_decay)
         super().__init__(field_size, feature_size, embedding_size, batch_size, l2_reg, learning_rate, optimizer,
                          update_mode, device, seed, world, epoch_steps)
 
@@ -29,7 +30,8 @@ class PNN(CTRModel):
         f32 = dict(dtype=torch.float32, device=dev)
         P = F * (F - 1) // 2                       # py2 integer division (quirk Q8, PNN.py:113)
         self.Dz = F * K + {"FNN": 0, "Inner": P, "Outer": P * K * K}[self.model_type]
-        self.mlp = MLP(self.Dz, self.layers, self.keep, B, dev, seed=self.seed)
+        self.mlp = MLP(self.Dz, self.layers, self.keep, B, dev, seed=self.seed, batch_norm=self.batch_norm,
+                       bn_decay=self.bn_decay)
         self.dense = DenseVars([("bias", (1,))] + self.mlp.specs(), self.opt, dev)
         self.mlp.init(self.dense, torch.Generator().manual_seed(self.seed))
         self.x = torch.empty(B, F * K, **f32)
