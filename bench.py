@@ -267,9 +267,18 @@ def main_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_graphs = world == 1 and os.environ.get("CTR_BENCH_GRAPHS", "1") != "0"
+
+    def train(ids, vals, labels):
+        # public API either way; the graphed form replays the step's launches from a CUDA graph (same kernels, same
+        # results: tests/test_gpu_deferred_headline.py::test_graph_replayed_steps_equal_eager_steps)
+        if use_graphs and model.update_mode == "exact_deferred":
+            return model.train_step_graphed(ids, vals, labels)
+        return model.train_step(ids, vals, labels)
+
     def step_dev(i):
         ids, vals, labels = devb[i % N_BATCHES]
-        model.train_step(ids, vals, labels)
+        train(ids, vals, labels)
 
     counts = {}
 
@@ -285,7 +294,7 @@ def main_b200(args):
         if model.updater.sweep_events is not None:
             model.updater.sweep_events = []
             model.updater.sweep_steps = []
-        counts["n0"] = _lib.launch_count()
+        counts["n0"] = _lib.launch_count() + getattr(model, "replayed_launches", 0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -293,7 +302,7 @@ def main_b200(args):
         if finish is not None:
             finish()
         e1.record()
-        counts["launches"] = _lib.launch_count() - counts["n0"]
+        counts["launches"] = _lib.launch_count() + getattr(model, "replayed_launches", 0) - counts["n0"]
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -343,7 +352,7 @@ def main_b200(args):
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[b])
         prefetch(i + 1)                              # other buffer: overlaps with this step's compute
-        parts = model.train_step(*bufs[b])
+        parts = train(*bufs[b])
         free[b].record(cur)
         loss_h[i % loss_h.shape[0]].copy_(parts, non_blocking=True)       # CE of this step
         if model.epoch_pos == 0 and not sharded:                          # L2 terms of the epoch just closed
@@ -374,7 +383,7 @@ def main_b200(args):
             zb = [tuple(t.to(dev) for t in synth.criteo_batch(B, N, F, seed=7000 + i, zipf=1.05)) for i in range(N_BATCHES)]
 
             def step_zipf(i):
-                model.train_step(*zb[i % N_BATCHES])
+                train(*zb[i % N_BATCHES])
             ms_z = timed(step_zipf, 2 * EPOCH, 3, finish=model.flush)
             extras["zipf_1.05"] = {"value": world * B * 2 * EPOCH / (ms_z * 1e-3), "unit": "samples/s",
                                    "ms_per_step": ms_z / (2 * EPOCH),
@@ -403,7 +412,7 @@ def main_b200(args):
             dst.copy_(src, non_blocking=True)
             ids_t, vals_t, labels_t, consumed, needs_host = _ops.parse_libsvm_device(dst, F, B, final_chunk=True)
             assert not needs_host and ids_t.shape[0] == B
-            parts = model.train_step(ids_t, vals_t, labels_t)
+            parts = train(ids_t, vals_t, labels_t)
             loss_t.copy_(parts, non_blocking=True)
         ms_t = timed(step_text, 2 * EPOCH, 3, finish=model.flush)
         extras["e2e_text"] = {"value": world * B * 2 * EPOCH / (ms_t * 1e-3), "unit": "samples/s",

@@ -37,7 +37,8 @@ def test_bn_kernels_match_fp64_autograd(n, H, keep):
     out = torch.empty(n, H, device=dev); sm = torch.empty(H, device=dev); sv = torch.empty(H, device=dev)
     md = mask.to(dev) if mask is not None else None
     ops.bn_fwd(xd, gd, bd, mm, mv, True, 0.9, md, keep, out, sm, sv)
-    _close(out, y64.detach(), 2e-6, "bn forward")
+    # n == 1: x == mean, and TF's x*inv + (beta - mean*inv) cancels to within an ulp of x*inv rather than exactly
+    _close(out, y64.detach(), 2e-6 if n > 1 else 1e-5, "bn forward")
     _close(mm, mm64, 2e-6, "moving_mean"); _close(mv, mv64, 2e-6, "moving_variance")
     dx = torch.empty(n, H, device=dev); dg = torch.empty(H, device=dev); db = torch.empty(H, device=dev)
     ops.bn_bwd(d_out.to(dev), xd, sm, sv, gd, md, keep, dx, dg, db)

@@ -50,6 +50,29 @@ def test_headline_config_bit_identical_2e7_rows():
     _run(a, b, 16 + 16 + 7, check_at=(15, 20, 31, 38), flush_at=(20, 34))
 
 
+@pytest.mark.parametrize("mode,P", [("exact_deferred", 4), ("lazy", 1), ("exact", 1)])
+def test_graph_replayed_steps_equal_eager_steps(mode, P):
+    """train_step_graphed (one CUDA graph per epoch position) must leave exactly the bits of train_step."""
+    from tf_repos_b200 import synth
+    from tf_repos_b200.deepfm import DeepFM
+    kw = dict(deep_layers="64,32", dropout="0.5,0.5", l2_reg=1e-4, learning_rate=5e-4, optimizer="Adam", device="cuda:0")
+    a = DeepFM(39, 50_000, 16, 512, update_mode=mode, epoch_steps=P, **kw)
+    b = DeepFM(39, 50_000, 16, 512, update_mode=mode, epoch_steps=P, **kw)
+    b.fm_v.var.copy_(a.fm_v.var); b.fm_w.var.copy_(a.fm_w.var); b.dense.flat.copy_(a.dense.flat)
+    for step in range(3 * max(P, 2) + 1):
+        ids, vals, labels = synth.criteo_batch(512, 50_000, 39, seed=step, device="cuda")
+        la = a.train_step(ids, vals, labels).clone()
+        lb = b.train_step_graphed(ids, vals, labels).clone()
+        assert torch.equal(la[0], lb[0]), f"CE differs at step {step}"
+    assert len(b._graphs) >= 1
+    a.flush(); b.flush()
+    for ta, tb in ((a.fm_v, b.fm_v), (a.fm_w, b.fm_w)):
+        assert torch.equal(ta.var, tb.var)
+        for sa, sb in zip(ta.slots, tb.slots):
+            assert torch.equal(sa, sb)
+    assert torch.equal(a.dense.flat, b.dense.flat) and a.global_step == b.global_step
+
+
 def _park(model, kind, seed):
     """Overwrite the tables' state with what rows nothing gathers look like after a long run."""
     g = torch.Generator(device="cuda").manual_seed(seed)

@@ -37,6 +37,7 @@ def floats(s) -> List[float]:
 
 
 class CTRModel:
+    replayed_launches = 0               # kernels launched through CUDA-graph replays (train_step_graphed)
     batch_norm, bn_decay = False, 0.9   # --batch_norm / --batch_norm_decay (set by the sub-class before _build)
     table_name = "emb"          # TF variable name of the [N,K] table
     linear_name: Optional[str] = None  # TF variable name of the [N] first-order table, if any
@@ -212,6 +213,50 @@ class CTRModel:
         return torch.cat(parts)
 
     bias_name: Optional[str] = None
+
+    # ---- CUDA-graph replay of the step ----------------------------------------------------------------------
+    def train_step_graphed(self, ids: torch.Tensor, vals: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """train_step with the ~45 kernel launches of a step replayed from a CUDA graph (one graph per position in
+        the epoch: the position is a launch argument of the row kernels).  Same kernels, same order, same results;
+        what goes away is the per-launch host latency between them.  Full batches on one GPU only; the step that
+        ends an epoch (it launches the table sweep) runs eagerly.  The returned tensor is the graph's static output:
+        it is overwritten by the next replay of the same position."""
+        B = ids.shape[0]
+        deferred = self.update_mode == "exact_deferred"
+        ends_epoch = deferred and self.epoch_pos == self.epoch_steps - 1
+        if B != self.B or self.world != 1 or ends_epoch:
+            return self.train_step(ids, vals, labels)
+        if not hasattr(self, "_graphs"):
+            self._graphs, self._graph_out, self._graph_seen = {}, {}, {}
+            self._gin = (torch.empty(self.B, self.F, dtype=torch.int32, device=self.device),
+                         torch.empty(self.B, self.F, dtype=torch.float32, device=self.device),
+                         torch.empty(self.B, dtype=torch.float32, device=self.device))
+        for dst, src in zip(self._gin, (ids, vals, labels)):
+            dst.copy_(src, non_blocking=True)
+        key = (self.update_mode, self.epoch_pos if deferred else 0)
+        g = self._graphs.get(key)
+        if g is None:
+            if not self._graph_seen.get(key):       # first visit: eager (lazy allocations, cudaFuncSetAttribute, ...)
+                self._graph_seen[key] = True
+                return self.train_step(*self._gin)
+            from . import _lib
+            pos, step = self.epoch_pos, self.global_step
+            n0 = _lib.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.train_step(*self._gin)
+            # capture ran the host code (bookkeeping advanced) but launched nothing: rewind, then replay below
+            self.epoch_pos, self.global_step = pos, step
+            self._graphs[key], self._graph_out[key] = g, out
+            self._graph_launches = getattr(self, "_graph_launches", {})
+            self._graph_launches[key] = _lib.launch_count() - n0     # kernels of libctr_b200.so inside this graph
+            self.replayed_launches -= self._graph_launches[key]      # the capture itself launched nothing
+        g.replay()
+        self.replayed_launches += self._graph_launches[key]
+        self.global_step += 1
+        if deferred:
+            self.epoch_pos += 1
+        return self._graph_out[key]
 
     def loss_value(self, parts: torch.Tensor) -> float:
         total = 0.0

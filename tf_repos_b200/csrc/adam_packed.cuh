@@ -46,11 +46,12 @@ constexpr float PK_SC48 = 281474976710656.f /* 2^48 */, PK_ISC24 = 5.96046447753
 constexpr float PK_S_A_HI = 7.2759576e-12f /* 2^-37 */, PK_S_V_HI = 2.2204460e-16f /* 2^-52 */;
 constexpr float PK_S_EPS_LO = 9.0949470e-13f /* 2^-40 */, PK_S_EPS_HI = 1.4901161e-8f /* 2^-26 */;
 
-// One step for one pair.  nlr = -lr_t.  trk_a: running min (MODE 0) / max (MODE 1,2) of |lr_t*m|;
-// trk_v: running min of v (MODE 0,1; unused in MODE 2).
+// One step for one pair.  nlr = -lr_t.  trk_a: running min (MODE 0) / max (MODE 1,2) of |lr_t*m|.
+// The second moment needs no per-step tracker: v' = b2*v + (1-b2)*g^2 >= RN(b2*v), so every v_s is bounded below
+// by the FIRST updated value times b2^(s-1) and above by the LAST one divided by b2^(n-s) (pk_valid).
 template <int MODE>
 __device__ __forceinline__ void adam_pk_step(float2& x, float2& m, float2& v, float nlr, const AdamPk& c,
-                                             float& trk_a, float& trk_v) {
+                                             float& trk_a) {
   const float2 NZ = bc2(c.nz);
   const float2 g = __fmul2_rn(bc2(c.l2), x);
   m = __fadd2_rn(__ffma2_rn(m, bc2(c.b1), NZ), __ffma2_rn(g, bc2(c.omb1), NZ));
@@ -73,7 +74,6 @@ __device__ __forceinline__ void adam_pk_step(float2& x, float2& m, float2& v, fl
     const float2 e = __ffma2_rn(neg2(y), y, v);
     const float2 sq = __ffma2_rn(e, hh, y);
     b = __fadd2_rn(sq, bc2(c.eps));
-    trk_v = fminf(fminf(trk_v, v.x), v.y);
   }
   float2 rc = make_float2(mufu_rcp(b.x), mufu_rcp(b.y));
   const float2 e2 = __ffma2_rn(neg2(b), rc, bc2(1.f));
@@ -98,12 +98,13 @@ __device__ __forceinline__ void adam_pk_step(float2& x, float2& m, float2& v, fl
 // NP pairs, steps [s0, s1) with nlr_s[s] = -lr_t of step s; q2[s-s0]... the caller accumulates sum(var^2)
 // through `ssq(s, value)`.
 struct PkTrackers {
-  float a, v;
+  float a;    // running min (MODE 0) / max (MODE 1, 2) of |lr_t*m|
+  float v1;   // min over the elements of the second moment after the FIRST step (set by the caller)
 };
 template <int MODE> __device__ __forceinline__ PkTrackers pk_trackers_init() {
   PkTrackers t;
   t.a = (MODE == 0) ? 3.0e38f : 0.f;
-  t.v = 3.0e38f;
+  t.v1 = 3.0e38f;
   return t;
 }
 
@@ -114,8 +115,10 @@ __device__ __forceinline__ bool pk_valid(const PkTrackers& t, float vfin_max, bo
   // v_s <= v_final / b2^(n-s) (the second moment cannot fall faster than b2 per step): bound every v_s from the last one
   const float vhi = (MODE == 0 ? SQRT_HI : PK_S_V_HI) * b2n * 0.99f;
   bool ok = x_finite && vfin_max <= vhi;
-  if (MODE == 0) ok = ok && t.a >= DIV_LO && t.v >= SQRT_LO;
-  if (MODE == 1) ok = ok && t.a <= PK_S_A_HI && t.v >= SQRT_LO;
+  // v_s >= v_1 * b2^(s-1) * (1 - 2^-24)^(s-1): demand v_1 * b2^n >= 1.01 * 2^-101
+  const bool v_lo_ok = t.v1 * b2n >= SQRT_LO * 1.01f;
+  if (MODE == 0) ok = ok && t.a >= DIV_LO && v_lo_ok;
+  if (MODE == 1) ok = ok && t.a <= PK_S_A_HI && v_lo_ok;
   if (MODE == 2) ok = ok && t.a <= PK_S_A_HI;
   return ok;
 }

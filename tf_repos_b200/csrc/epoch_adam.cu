@@ -47,14 +47,26 @@ __device__ __forceinline__ bool pk_run(float2 (&x)[NP], float2 (&m)[NP], float2 
                                        const SweepSmem& sm, int from, int upto, float b2n,
                                        const float2* w = nullptr) {
   PkTrackers t = pk_trackers_init<MODE>();
-#pragma unroll 1
-  for (int s = from; s < upto; ++s) {
+  // first step apart: its second moments give the lower bound of the whole trajectory's (pk_valid)
+  {
+    const float nlr = sm.nlr[from];
+    float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      q2 = __ffma2_rn(WEIGHTED ? __fmul2_rn(x[p], w[p]) : x[p], x[p], q2);
+      adam_pk_step<MODE>(x[p], m[p], v[p], nlr, c, t.a);
+      t.v1 = fminf(fminf(t.v1, v[p].x), v[p].y);
+    }
+    sm.ss_tmp[threadIdx.x] = q2.x + q2.y;
+  }
+#pragma unroll 2
+  for (int s = from + 1; s < upto; ++s) {
     const float nlr = sm.nlr[s];
     float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       q2 = __ffma2_rn(WEIGHTED ? __fmul2_rn(x[p], w[p]) : x[p], x[p], q2);
-      adam_pk_step<MODE>(x[p], m[p], v[p], nlr, c, t.a, t.v);
+      adam_pk_step<MODE>(x[p], m[p], v[p], nlr, c, t.a);
     }
     sm.ss_tmp[(s - from) * SWEEP_THREADS + threadIdx.x] = q2.x + q2.y;
   }

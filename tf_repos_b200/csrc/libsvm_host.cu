@@ -59,9 +59,19 @@ int64_t ctr_parse_libsvm(const char* buf, size_t len, int F, int64_t max_rows, i
         set_error("ctr_parse_libsvm: row %lld field %d: expected <id>:<val>", (long long)row, f);
         return CTR_ERR_INVALID_ARG;
       }
+      if (id < (long)INT32_MIN || id > (long)INT32_MAX) {   // tf.string_to_number(out_type=int32) raises (DeepFM.py:74)
+        set_error("ctr_parse_libsvm: row %lld field %d: id %ld is outside the int32 range", (long long)row, f, id);
+        return CTR_ERR_INVALID_ARG;
+      }
       p = q + 1;
+      // strtof skips leading white space, newlines included: an empty value ("3:" at the end of a line, "3: 0.5")
+      // must not swallow the next token / the next line's label
+      if (p >= e || *p == ' ' || *p == '\t') {
+        set_error("ctr_parse_libsvm: row %lld field %d: empty value", (long long)row, f);
+        return CTR_ERR_INVALID_ARG;
+      }
       const float v = strtof(p, &q);
-      if (q == p) {
+      if (q == p || q > e) {
         set_error("ctr_parse_libsvm: row %lld field %d: value is not a number", (long long)row, f);
         return CTR_ERR_INVALID_ARG;
       }

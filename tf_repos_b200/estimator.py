@@ -133,8 +133,10 @@ def run(build_model: Callable[[], object], model_name: str):
         t0, s0 = time.time(), model.global_step
         last = None
         for ids, vals, labels in batches(tr_files, FLAGS.num_epochs):
-            last = model.train_step(ids, vals, labels)
+            step_fn = getattr(model, "train_step_graphed", model.train_step)   # full batches replay a CUDA graph
+            last = step_fn(ids, vals, labels)
             if model.global_step % FLAGS.log_steps == 0:
+                model.check_ids()       # TF fails on the first bad batch; here: at the next log point, before more damage
                 dt = time.time() - t0
                 print("INFO:global_step/sec: %g  samples/sec: %g" % ((model.global_step - s0) / dt,
                                                                       (model.global_step - s0) * FLAGS.batch_size / dt))
