@@ -322,6 +322,14 @@ int ctr_dropout_apply(const float* x, const float* mask, float keep, int64_t n, 
 int ctr_a2a_bucket_ids(const int32_t* uniq, const int32_t* n_uniq, int64_t n_max, int G, int32_t* counts,
                        int32_t* cursor, int32_t* order, int32_t* pos_of, int32_t* local_ids, ctr_stream_t stream);
 int ctr_remap_ids(const int32_t* inverse, const int32_t* pos_of, int64_t n, int32_t* out, ctr_stream_t stream);
+/* Composite routing keys (what tf_repos_b200/sharded.py uses): key(id) = (id % G) * ceil(N/G) + id / G, so that ONE
+ * ctr_unique_segment of the keys yields the unique ids in bucket order (owner-major, ascending id inside an owner),
+ * `inverse` = the occurrence's position in the received row cache, and perm / seg_offsets = the gradient segments in
+ * cache order.  ids outside [0, N) are counted in oob (may be NULL) and routed to row 0.
+ * shard_split: counts[o] = unique ids owned by rank o, local_ids[u] = local row of the u-th unique key. */
+int ctr_shard_keys(const int32_t* ids, int64_t n, int64_t N, int G, int32_t* keys, int32_t* oob, ctr_stream_t stream);
+int ctr_shard_split(const int32_t* uniq_keys, const int32_t* n_uniq, int64_t n_max, int64_t N, int G, int32_t* counts,
+                    int32_t* local_ids, ctr_stream_t stream);
 int ctr_gather_scalar(const int32_t* ids, const float* W, int64_t N, int64_t n, float* out, ctr_stream_t stream);
 
 /* ---- wide_n_deep feature columns (wide_n_deep.py:92-107) ------------------------------------

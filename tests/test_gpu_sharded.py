@@ -37,6 +37,21 @@ def test_bucket_kernels_match_plan(G):
     remap = torch.empty(n, **i32)
     ops.remap_ids(torch.from_numpy(inverse.astype(np.int32)).to(d), pos_of, n, remap)
     assert np.array_equal(uniq[o][remap.cpu().numpy()], ids)
+    # composite routing keys: one sort gives the same plan, deterministically
+    from tf_repos_b200.ops import UniqueWorkspace
+    N = 50_000
+    npad = (N + G - 1) // G
+    keys = torch.empty(n, **i32)
+    ops.shard_keys(torch.from_numpy(ids).to(d), N, G, keys)
+    assert np.array_equal(keys.cpu().numpy(), (ids % G) * npad + ids // G)
+    uw = UniqueWorkspace(n, G * npad, d)
+    ops.unique_segment(keys, uw)
+    counts2 = torch.zeros(G, **i32); local2 = torch.empty(n, **i32)
+    ops.shard_split(uw.uniq, uw.n_uniq, n, N, G, counts2, local2)
+    assert uw.n_uniq.item() == U and counts2.tolist() == ref_counts.tolist()
+    assert np.array_equal(local2[:U].cpu().numpy(), ref_local)                    # bucket-major, ascending id inside
+    cache_ids = ref_local * G + np.repeat(np.arange(G), ref_counts)               # global id of every cache position
+    assert np.array_equal(cache_ids[uw.inverse[:n].cpu().numpy()], ids)           # inverse == cache position
     W = torch.randn(50_000, device=d); out = torch.empty(n, device=d)
     ops.gather_scalar(torch.from_numpy(ids).to(d), W, out)
     assert torch.equal(out, W[torch.from_numpy(ids).long().to(d)])

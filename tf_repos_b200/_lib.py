@@ -88,6 +88,8 @@ SIGNATURES = {
     "ctr_dropout_apply": (c_int, [P, P, c_float, c_int64, P, P]),
     "ctr_a2a_bucket_ids": (c_int, [P, P, c_int64, c_int, P, P, P, P, P, P]),
     "ctr_remap_ids": (c_int, [P, P, c_int64, P, P]),
+    "ctr_shard_keys": (c_int, [P, c_int64, c_int64, c_int, P, P, P]),
+    "ctr_shard_split": (c_int, [P, P, c_int64, c_int64, c_int, P, P, P]),
     "ctr_gather_scalar": (c_int, [P, P, c_int64, c_int64, P, P]),
     "ctr_wd_input_fwd": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "ctr_wd_input_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P]),

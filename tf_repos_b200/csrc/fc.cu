@@ -127,6 +127,18 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, i
   }
 }
 
+// out[k][n] = sum_z partial[z][n][k]: reduce split-R partials of the TRANSPOSED product (dW^T = dZ^T @ in)
+__global__ void splitk_reduce_t_kernel(const float* __restrict__ partial, int S, int Kd, int Nd, float* __restrict__ out) {
+  const int64_t n = (int64_t)Kd * Nd;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int k = (int)(i / Nd), c = (int)(i % Nd);
+    float s = 0.f;
+    for (int z = 0; z < S; ++z) s += partial[(int64_t)z * n + (int64_t)c * Kd + k];
+    out[i] = s;
+  }
+}
+
 // dZ = (dOut * mask / keep) * (out > 0) in place, plus partial column sums (bias gradient)
 constexpr int DZ_ROWS = 128;
 __global__ void __launch_bounds__(256)
@@ -318,8 +330,17 @@ int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* 
   splitk_reduce_kernel<<<(Nd + 255) / 256, 256, 0, st>>>(colsum, chunks, Nd, db);
   CTR_LAUNCHED("fc_db_reduce");
   // 2. dW[Kd,Nd] = in^T @ dZ, split over M
-  const int S = pick_split(Kd, Nd, M);
-  {
+  // narrow layer input (DIN attention: Kd = 32, Nd = 256, M = B*P = 409600): as in^T @ dZ the 128-row MMA tile
+  // would be 3/4 padding; the transposed product dW^T[Nd,Kd] = dZ^T @ in fills it (and its N = Kd MMAs are 4x smaller)
+  const bool dw_transposed = use_tc() && Kd <= 64 && Nd >= 128;
+  const int S = dw_transposed ? pick_split(Nd, Kd, M) : pick_split(Kd, Nd, M);
+  if (dw_transposed) {
+    tc_gemm_dispatch(2, 0, dOut, Nd, in, Kd, dw_part, Kd, Nd, Kd, M, S, nullptr, 0, nullptr, 1.f, nullptr, 1, st);
+    CTR_LAUNCHED("fc_dw(t)");
+    const int64_t n = (int64_t)Kd * Nd;
+    splitk_reduce_t_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dw_part, S, Kd, Nd, dW);
+    CTR_LAUNCHED("fc_dw_reduce(t)");
+  } else {
     if (use_tc()) {
       tc_gemm_dispatch(2, 0, in, Kd, dOut, Nd, S == 1 ? dW : dw_part, Nd, Kd, Nd, M, S, nullptr, 0, nullptr, 1.f, nullptr, 1, st);
     } else {

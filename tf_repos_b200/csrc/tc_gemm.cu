@@ -18,6 +18,8 @@
 //                   whole rows per warp: bias / group bias / relu / dropout / accumulate -> 512 B coalesced stores
 // Operands are staged by plain loads rather than TMA because the three products of a layer need
 // three different operand orientations of fp32 data that must be split anyway.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ctr {
@@ -311,6 +313,272 @@ tc_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
   }
 }
 
+
+// ================================================================================================================
+// Warp-specialised variant (reductions of >= 3 slices): 8 producer warps, 1 MMA warp, 3-stage mbarrier ring.
+//   producers (warps 0-7, 256 threads): global -> registers (two slices ahead) -> hi/lo split -> swizzled st.shared
+//       -> fence.proxy.async -> arrive on full[s]; before refilling a stage they wait on empty[s]
+//   MMA warp (warp 8, one elected lane): wait full[s] -> 12 x tcgen05.mma (3xTF32, two accumulators) ->
+//       tcgen05.commit -> empty[s]; after the last slice a commit on accum_done
+//   epilogue: warps 0-3 drain TMEM (lane quarter = warp) into the staging tile, then all 8 producer warps write rows.
+// No __syncthreads inside the main loop: staging of slice k+1.. overlaps the tensor core working on slice k.
+// ================================================================================================================
+constexpr int WS_PROD = 256, WS_THREADS = WS_PROD + 32, WS_STAGES = 3;
+
+template <bool RC>
+__device__ __forceinline__ void ws_load_tile(float4 (&r)[4], const float* __restrict__ P, int ld, int row0, int n_rows,
+                                             int r0, int r_end, int tid) {
+  if (RC) {
+    const int sub = (tid & 31) >> 3, ch = tid & 7, wrow = (tid >> 5) * 16;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int g = row0 + wrow + it * 4 + sub, k0 = r0 + ch * 4;
+      const float* p = P + (int64_t)g * ld + k0;
+      if (g < n_rows && k0 + 4 <= r_end && ((((uintptr_t)p) & 15) == 0)) {
+        r[it] = __ldg(reinterpret_cast<const float4*>(p));
+      } else {
+        const bool in = g < n_rows;
+        r[it].x = (in && k0 < r_end) ? p[0] : 0.f;
+        r[it].y = (in && k0 + 1 < r_end) ? p[1] : 0.f;
+        r[it].z = (in && k0 + 2 < r_end) ? p[2] : 0.f;
+        r[it].w = (in && k0 + 3 < r_end) ? p[3] : 0.f;
+      }
+    }
+  } else {
+    const int g = row0 + (tid & 127), half = tid >> 7;
+    const bool in = g < n_rows;
+    const float* p = P + (int64_t)r0 * ld + g;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int cc = half * 4 + c;
+      r[c].x = (in && r0 + 4 * cc < r_end) ? p[(int64_t)(4 * cc) * ld] : 0.f;
+      r[c].y = (in && r0 + 4 * cc + 1 < r_end) ? p[(int64_t)(4 * cc + 1) * ld] : 0.f;
+      r[c].z = (in && r0 + 4 * cc + 2 < r_end) ? p[(int64_t)(4 * cc + 2) * ld] : 0.f;
+      r[c].w = (in && r0 + 4 * cc + 3 < r_end) ? p[(int64_t)(4 * cc + 3) * ld] : 0.f;
+    }
+  }
+}
+
+template <bool RC>
+__device__ __forceinline__ void ws_store_tile(const float4 (&r)[4], uint8_t* hi_tile, uint8_t* lo_tile, int tid) {
+  const int sub = (tid & 31) >> 3, ch = tid & 7, wrow = (tid >> 5) * 16;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = RC ? (wrow + it * 4 + sub) : (tid & 127);
+    const int chunk = RC ? ch : ((tid >> 7) * 4 + it);
+    float4 hi, lo;
+    hi.x = tf32_hi(r[it].x); hi.y = tf32_hi(r[it].y); hi.z = tf32_hi(r[it].z); hi.w = tf32_hi(r[it].w);
+    lo.x = r[it].x - hi.x; lo.y = r[it].y - hi.y; lo.z = r[it].z - hi.z; lo.w = r[it].w - hi.w;
+    const uint32_t off = sw128_off(row, chunk);
+    *reinterpret_cast<float4*>(hi_tile + off) = hi;
+    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_ws(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WS_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WS_DONE;\n\t"
+      "bra WS_WAIT_LOOP;\n\t"
+      "WS_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void prod_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <bool A_RC, bool B_RC, int EPI>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+tc_gemm_ws_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C,
+                  int ldc, int M, int N, int R, const float* __restrict__ bias, int act, const float* __restrict__ mask,
+                  float keep, const float* __restrict__ gbias, int gP) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[WS_STAGES], bar_empty[WS_STAGES], bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int i0 = blockIdx.y * TC_BM, j0 = blockIdx.x * TC_BM;
+  const int n_here = min(N - j0, TC_BM);
+  const int n_pad = (n_here + 15) & ~15;
+  const int r_chunk = (R + gridDim.z - 1) / gridDim.z;
+  const int r_begin = blockIdx.z * r_chunk, r_end = min(R, r_begin + r_chunk);
+  const int KT = max((r_end - r_begin + TC_BK - 1) / TC_BK, 0);
+
+  if (tid == 0) {
+    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&bar_full[s], WS_PROD); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 8) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0 && KT > 0) {
+      const uint32_t idesc = make_idesc(TC_BM, n_pad);
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % WS_STAGES;
+        mbar_wait_ws(&bar_full[s], (uint32_t)((kt / WS_STAGES) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(smem + s * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES,
+                       b_lo = a_hi + 3 * TC_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint32_t ko = k * 32;
+          const uint32_t first = (kt > 0 || k > 0) ? 1u : 0u;
+          umma_tf32(tmem_d + 128, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, first);
+          umma_tf32(tmem_d + 128, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
+          umma_tf32(tmem_d, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, first);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_empty[s])) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_done)) : "memory");
+    }
+    return;
+  }
+
+  // ---------------- producers ----------------
+  {
+    float4 ra[2][4], rb[2][4];
+    if (KT > 0) { ws_load_tile<A_RC>(ra[0], A, lda, i0, M, r_begin, r_end, tid); ws_load_tile<B_RC>(rb[0], B, ldb, j0, N, r_begin, r_end, tid); }
+    if (KT > 1) { ws_load_tile<A_RC>(ra[1], A, lda, i0, M, r_begin + TC_BK, r_end, tid); ws_load_tile<B_RC>(rb[1], B, ldb, j0, N, r_begin + TC_BK, r_end, tid); }
+    for (int kt0 = 0; kt0 < KT; kt0 += 2) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kt = kt0 + u;
+        if (kt < KT) {
+          const int s = kt % WS_STAGES;
+          if (kt >= WS_STAGES) mbar_wait_ws(&bar_empty[s], (uint32_t)(((kt / WS_STAGES) - 1) & 1));
+          uint8_t* st = smem + s * TC_STAGE_BYTES;
+          ws_store_tile<A_RC>(ra[u], st, st + TC_TILE_BYTES, tid);
+          ws_store_tile<B_RC>(rb[u], st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, tid);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&bar_full[s]);
+          if (kt + 2 < KT) {
+            const int r0 = r_begin + (kt + 2) * TC_BK;
+            ws_load_tile<A_RC>(ra[u], A, lda, i0, M, r0, r_end, tid);
+            ws_load_tile<B_RC>(rb[u], B, ldb, j0, N, r0, r_end, tid);
+          }
+        }
+      }
+    }
+  }
+  if (KT > 0) mbar_wait_ws(&bar_done, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---------------- epilogue 1 (warps 0-3): TMEM -> registers -> staging tile ----------------
+  float* stg = reinterpret_cast<float*>(smem);
+  if (warp < 4) {
+    for (int c0 = 0; c0 < n_pad; c0 += 16) {
+      uint32_t r[16], r2[16];
+      if (KT > 0) {
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]), "=r"(r2[8]),
+              "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15])
+            : "r"(taddr + 128));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 16; ++q) r[q] = __float_as_uint(__uint_as_float(r[q]) + __uint_as_float(r2[q]));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) r[q] = 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 16; q += 4)
+        *reinterpret_cast<uint4*>(stg + tid * TC_STG_PITCH + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  prod_bar_sync();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256));
+
+  // ---------------- epilogue 2 (warps 0-7): whole rows, 512 B coalesced stores ----------------
+  float* Cz = C + (EPI == 0 ? (int64_t)blockIdx.z * M * ldc : 0);
+  const int col = lane * 4, gj = j0 + col;
+  const bool vec = ((ldc & 3) == 0) && ((((uintptr_t)Cz) & 15) == 0) && (EPI != 1 || !mask || ((((uintptr_t)mask) & 15) == 0));
+  if (col < n_here) {
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (EPI == 1 && bias) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bv[q] = (gj + q < N) ? bias[gj + q] : 0.f;
+    }
+    const int rows = min(TC_BM, M - i0);
+    for (int row = warp; row < rows; row += 8) {
+      const int gi = i0 + row;
+      const float4 t = *reinterpret_cast<const float4*>(stg + row * TC_STG_PITCH + col);
+      float v[4] = {t.x, t.y, t.z, t.w};
+      float* cp = Cz + (int64_t)gi * ldc + gj;
+      const bool full = vec && (col + 4 <= n_here);
+      if (EPI == 2) {
+        if (full) { const float4 o = *reinterpret_cast<const float4*>(cp); v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
+        else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (col + q < n_here) v[q] += cp[q];
+        }
+      }
+      if (EPI == 1) {
+        const float* gb = gbias ? gbias + (int64_t)(gi / gP) * N + gj : nullptr;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[q] += bv[q];
+          if (gb && col + q < n_here) v[q] += gb[q];
+          if (act == 1) v[q] = fmaxf(v[q], 0.f);
+        }
+        if (mask) {
+          const float* mp = mask + (int64_t)gi * ldc + gj;
+          if (full) {
+            const float4 mk = *reinterpret_cast<const float4*>(mp);
+            v[0] = __fdiv_rn(v[0], keep) * mk.x; v[1] = __fdiv_rn(v[1], keep) * mk.y;
+            v[2] = __fdiv_rn(v[2], keep) * mk.z; v[3] = __fdiv_rn(v[3], keep) * mk.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (col + q < n_here) v[q] = __fdiv_rn(v[q], keep) * mp[q];
+          }
+        }
+      }
+      if (full) {
+        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (col + q < n_here) cp[q] = v[q];
+      }
+    }
+  }
+}
+
+template <bool A_RC, bool B_RC, int EPI>
+static int launch_tc_ws(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int R, int S,
+                        const float* bias, int act, const float* mask, float keep, const float* gbias, int gP,
+                        cudaStream_t st) {
+  static bool attr = false;
+  constexpr int smem = WS_STAGES * TC_STAGE_BYTES + 1024;
+  if (!attr) {
+    cudaFuncSetAttribute(tc_gemm_ws_kernel<A_RC, B_RC, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  dim3 grid((N + TC_BM - 1) / TC_BM, (M + TC_BM - 1) / TC_BM, S);
+  tc_gemm_ws_kernel<A_RC, B_RC, EPI><<<grid, WS_THREADS, smem, st>>>(A, lda, B, ldb, C, ldc, M, N, R, bias, act, mask, keep,
+                                                                    gbias, gP);
+  return 0;
+}
+
 template <bool A_RC, bool B_RC, int EPI, int STAGES>
 static int launch_tc_s(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int R, int S,
                        const float* bias, int act, const float* mask, float keep, const float* gbias, int gP,
@@ -332,6 +600,11 @@ static int launch_tc(const float* A, int lda, const float* B, int ldb, float* C,
                      const float* bias, int act, const float* mask, float keep, const float* gbias, int gP,
                      cudaStream_t st) {
   const int r_chunk = (R + S - 1) / S;
+  // CTR_GEMM_WS=0 keeps the single-role kernel for every shape (A/B switch, tools/bench_gemm.py)
+  static int ws = -1;
+  if (ws < 0) { const char* e = getenv("CTR_GEMM_WS"); ws = e ? atoi(e) : 1; }
+  if (ws && r_chunk >= 3 * TC_BK)
+    return launch_tc_ws<A_RC, B_RC, EPI>(A, lda, B, ldb, C, ldc, M, N, R, S, bias, act, mask, keep, gbias, gP, st);
   if (r_chunk <= TC_BK)
     return launch_tc_s<A_RC, B_RC, EPI, 1>(A, lda, B, ldb, C, ldc, M, N, R, S, bias, act, mask, keep, gbias, gP, st);
   return launch_tc_s<A_RC, B_RC, EPI, 2>(A, lda, B, ldb, C, ldc, M, N, R, S, bias, act, mask, keep, gbias, gP, st);

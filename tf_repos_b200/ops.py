@@ -364,6 +364,17 @@ def remap_ids(inverse, pos_of, n, out):
           "ctr_remap_ids")
 
 
+def shard_keys(ids, N: int, G: int, keys, oob=None):
+    check(_L.ctr_shard_keys(_p(ids, torch.int32, "ids"), ids.numel(), N, G, _p(keys, torch.int32, "keys"),
+                            _p(oob, torch.int32, "oob"), _stream()), "ctr_shard_keys")
+
+
+def shard_split(uniq_keys, n_uniq, n_max: int, N: int, G: int, counts, local_ids):
+    check(_L.ctr_shard_split(_p(uniq_keys, torch.int32, "uniq"), _p(n_uniq, torch.int32, "n_uniq"), n_max, N, G,
+                             _p(counts, torch.int32, "counts"), _p(local_ids, torch.int32, "local_ids"), _stream()),
+          "ctr_shard_split")
+
+
 def gather_scalar(ids, W, out):
     check(_L.ctr_gather_scalar(_p(ids, torch.int32, "ids"), _p(W, torch.float32, "W"), W.numel(), ids.numel(),
                                _p(out, torch.float32, "out"), _stream()), "ctr_gather_scalar")

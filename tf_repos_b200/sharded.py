@@ -65,12 +65,14 @@ class ShardedDeepFM:
         self.loss_ce = self.dense.tail[0:1]
         self.oob = torch.zeros(2, **i32)
         # requester side
-        self.uw = ops.UniqueWorkspace(n, self.N, dev)            # unique of my batch's global ids
-        self.uw2 = ops.UniqueWorkspace(n, n, dev)                # segment structure over cache positions
-        self.counts = torch.zeros(G, **i32); self.cursor = torch.zeros(G, **i32)
+        # unique of my batch's routing keys (owner * ceil(N/G) + local row): bucket order, cache positions and the
+        # gradient segments all come out of this one sort (csrc/shard.cu)
+        self.n_keys = G * ((self.N + G - 1) // G)
+        self.uw = ops.UniqueWorkspace(n, self.n_keys, dev)
+        self.keys = torch.empty(n, **i32)
+        self.counts = torch.zeros(G, **i32)
         self.count_mat = torch.zeros(G * G, **i32)
-        self.order = torch.empty(n, **i32); self.pos_of = torch.empty(n, **i32)
-        self.local_ids = torch.empty(n, **i32); self.ids_remap = torch.empty(n, **i32)
+        self.local_ids = torch.empty(n, **i32)
         self.cache_v = torch.empty(n, K, **f32); self.cache_w = torch.empty(n, **f32)
         self.g_cache = torch.empty(n, K, **f32); self.gw_cache = torch.empty(n, **f32)
         # owner side (worst case: every rank asks me for n rows)
@@ -120,10 +122,9 @@ class ShardedDeepFM:
     def _lookup(self, ids: torch.Tensor, deferred_j=None):
         """unique -> route -> fetch rows into the cache; returns (U, send_splits, recv_splits, R)."""
         G, n = self.G, ids.numel()
-        ops.unique_segment(ids.reshape(-1), self.uw)
-        ops.a2a_bucket_ids(self.uw.uniq, self.uw.n_uniq, n, G, self.counts, self.cursor, self.order, self.pos_of,
-                           self.local_ids)
-        ops.remap_ids(self.uw.inverse, self.pos_of, n, self.ids_remap[:n])
+        ops.shard_keys(ids.reshape(-1), self.N, G, self.keys[:n], self.oob)
+        ops.unique_segment(self.keys[:n], self.uw)          # uw.inverse[i] = cache position of occurrence i
+        ops.shard_split(self.uw.uniq, self.uw.n_uniq, n, self.N, G, self.counts, self.local_ids)
         if G > 1:   # every rank's bucket sizes in one collective, one host sync per step
             dist.all_gather_into_tensor(self.count_mat, self.counts, group=self.group)
             cm = self.count_mat.view(G, G).tolist()
@@ -145,7 +146,7 @@ class ShardedDeepFM:
 
     def _forward(self, ids, vals, U, train, masks=None):
         B = ids.shape[0]
-        rid = self.ids_remap[: B * self.F].view(B, self.F)
+        rid = self.uw.inverse[: B * self.F].view(B, self.F)
         ops.fm_embed_fwd(rid, vals, self.cache_v[:U], self.cache_w[:U], ops.FM_DEEPFM, x=self.x[:B], y_w=self.y_w[:B],
                          y2=self.y_v[:B], S=self.S[:B], oob=self.oob)
         self._a = self.mlp.forward_hidden(self.x[:B], self.dense, train, masks, step_dev=self.opt.state[3:4])
@@ -180,10 +181,8 @@ class ShardedDeepFM:
         self.mlp.backward_out(self._a, self.dy, self.dense, self.d_last)
         dX = self.mlp.backward_hidden(self.x, self.d_last, self.dense)
         ops.fm_embed_bwd(vals, self.x, self.S, dX, self.dy, self.dy, K, ops.FM_DEEPFM, self.g_rows, self.g_w)
-        # per cache row (bucket order == ascending remapped id)
-        self.uw2.N = max(U, 1)
-        ops.unique_segment(self.ids_remap[:n], self.uw2)
-        ops.segment_sum_rows(self.g_rows, self.g_w, self.uw2, K, self.g_cache, self.gw_cache)
+        # per cache row: the lookup's sort already grouped the occurrences in cache order
+        ops.segment_sum_rows(self.g_rows, self.g_w, self.uw, K, self.g_cache, self.gw_cache)
         self._a2a(self.recv_g[:R], self.g_cache[:U], recv, send)
         self._a2a(self.recv_gw[:R], self.gw_cache[:U], recv, send)
         if G > 1:
