@@ -175,6 +175,12 @@ int ctr_epoch_tick(float* state, float* hyper, int n_hyper, float* lr_table, int
 int ctr_epoch_rows(int opt, int apply, float* var, float* slot0, float* slot1, uint8_t* last,
                    const int32_t* uniq, const int32_t* n_uniq, const float* g_uniq, int64_t n_max, int K,
                    const float* hyper, const float* lr_table, int j, double* ss, ctr_stream_t stream);
+/* ctr_epoch_rows for the [N,K] table AND a scalar table [N] gathered with the same ids (fm_v + fm_w, DeepFM.py:115-116)
+ * in one launch; K in {4, 8, 16, 32, 64, 128, 256}.  Same arithmetic as two ctr_epoch_rows calls. */
+int ctr_epoch_rows2(int opt, int apply, float* var, float* slot0, float* slot1, uint8_t* last, float* w_var, float* w_slot0,
+                    float* w_slot1, uint8_t* w_last, const int32_t* uniq, const int32_t* n_uniq, const float* g_uniq,
+                    const float* gw_uniq, int64_t n_max, int K, const float* hyper, const float* lr_table, int j, double* ss,
+                    double* ss_w, ctr_stream_t stream);
 /* All rows -> state after `upto` steps of this epoch.  Rows whose `last` byte equals `from` (nothing gathered
  * them since the previous sweep; from = 0 after an epoch-end sweep) replay steps from..upto-1; the others replay
  * last..upto-1.  reset != 0: epoch end, every `last` byte returns to 0; reset == 0: mid-epoch flush, `last` = upto.

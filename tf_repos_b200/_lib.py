@@ -49,6 +49,7 @@ SIGNATURES = {
     "ctr_epoch_max_steps": (c_int, []),
     "ctr_epoch_tick": (c_int, [P, P, c_int, P, c_int, c_int, P]),
     "ctr_epoch_rows": (c_int, [c_int, c_int, P, P, P, P, P, P, P, c_int64, c_int, P, P, c_int, P, P]),
+    "ctr_epoch_rows2": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, P, P, c_int, P, P, P]),
     "ctr_epoch_sweep": (c_int, [c_int, P, P, P, P, c_int64, c_int, P, P, c_int, c_int, c_int, P,
                                 ctypes.POINTER(c_int), P, c_int64, P, P, P]),
     "ctr_epoch_reg_loss": (c_int, [P, P, c_int, c_int, c_float, P, c_int, P]),

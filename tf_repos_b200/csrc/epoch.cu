@@ -36,17 +36,23 @@ __device__ __forceinline__ float sq4(const float4& x) {
 // Rows uniq[0..n_uniq): replay the untouched-row step for steps last[row]..j-1 so that the stored
 // state is the state at the START of step j; then (APPLY) take step j with the summed gradient.
 // ss[s] (double) accumulates sum(var^2) of the state each replayed/applied step started from.
-template <int OPT, int LPR, int VEC, bool APPLY>
+// second scalar table gathered with the same ids (DeepFM: fm_w next to fm_v): lane 0 of a row carries its element
+struct RowsW {
+  float* var; float* slot0; float* slot1; uint8_t* last; const float* g_uniq; double* ss;
+};
+
+template <int OPT, int LPR, int VEC, bool APPLY, bool WITH_W = false>
 __global__ void __launch_bounds__(256)
 epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
                   uint8_t* __restrict__ last, const int32_t* __restrict__ uniq,
                   const int32_t* __restrict__ n_uniq, const float* __restrict__ g_uniq, int64_t n_max,
                   const float* __restrict__ hyper, const float* __restrict__ lr_table, int j,
-                  double* __restrict__ ss, int set_last) {
+                  double* __restrict__ ss, int set_last, RowsW w = RowsW()) {
   constexpr int K = 4 * LPR * VEC;
   constexpr bool two = OptTraits<OPT>::slots == 2;
   __shared__ float ss_blk[EPOCH_MAX];  // <= 256 rows' worth per CTA: fp32 is plenty; global sums are double
-  if (threadIdx.x < EPOCH_MAX) ss_blk[threadIdx.x] = 0.f;
+  __shared__ float ssw_blk[EPOCH_MAX];
+  if (threadIdx.x < EPOCH_MAX) { ss_blk[threadIdx.x] = 0.f; ssw_blk[threadIdx.x] = 0.f; }
   __syncthreads();
   const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int c = threadIdx.x % LPR;
@@ -65,8 +71,12 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
     a[v] = active ? *reinterpret_cast<const float4*>(slot0 + e) : f4_zero();
     b[v] = (active && two) ? *reinterpret_cast<const float4*>(slot1 + e) : f4_zero();
   }
+  const bool wact = WITH_W && active && c == 0;
+  int l0w = j;
+  float xw = 0.f, aw = 0.f, bw = 0.f;
+  if (wact) { l0w = w.last[id]; xw = w.var[id]; aw = w.slot0[id]; bw = two ? w.slot1[id] : 0.f; }
   // warp-uniform trip count (the body reduces across the warp); a lane joins at its own row's `last`
-  const int lmin = __reduce_min_sync(FULL_MASK, l0);
+  const int lmin = __reduce_min_sync(FULL_MASK, min(l0, l0w));
 #pragma unroll 1
   for (int s = lmin; s < j; ++s) {
     h.lr = lr_table[s];
@@ -83,6 +93,12 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
     }
     q = warp_sum(q);
     if (lane == 0 && q != 0.f) atomicAdd(&ss_blk[s], q);
+    if (WITH_W) {
+      float qw = 0.f;
+      if (wact && s >= l0w) { qw = xw * xw; step_sparse<OPT>(xw, aw, bw, __fmul_rn(h.l2, xw), h); }
+      qw = warp_sum(qw);
+      if (lane == 0 && qw != 0.f) atomicAdd(&ssw_blk[s], qw);
+    }
   }
   if (APPLY) {
     h.lr = lr_table[j];
@@ -99,7 +115,18 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
     }
     q = warp_sum(q);
     if (lane == 0 && q != 0.f) atomicAdd(&ss_blk[j], q);
+    if (WITH_W) {
+      float qw = 0.f;
+      if (wact) { qw = xw * xw; step_sparse<OPT>(xw, aw, bw, __fadd_rn(w.g_uniq[u], __fmul_rn(h.l2, xw)), h); }
+      qw = warp_sum(qw);
+      if (lane == 0 && qw != 0.f) atomicAdd(&ssw_blk[j], qw);
+    }
   }
+  if (WITH_W && wact && (APPLY || l0w < j)) {
+    w.var[id] = xw; w.slot0[id] = aw;
+    if (two) w.slot1[id] = bw;
+  }
+  if (WITH_W && wact && (APPLY || l0w < j || set_last >= 0)) w.last[id] = (uint8_t)(set_last >= 0 ? set_last : (APPLY ? j + 1 : j));
   const bool wrote = active && (APPLY || l0 < j);
   const uint8_t new_last = (uint8_t)(set_last >= 0 ? set_last : (APPLY ? j + 1 : j));
   if (wrote) {
@@ -114,6 +141,7 @@ epoch_rows_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __r
   __syncthreads();  // every lane of a row has read `last` before lane 0 of the row rewrites it
   if (active && c == 0 && (wrote || set_last >= 0)) last[id] = new_last;
   if (threadIdx.x < EPOCH_MAX && ss_blk[threadIdx.x] != 0.f) atomicAdd(&ss[threadIdx.x], (double)ss_blk[threadIdx.x]);
+  if (WITH_W && threadIdx.x < EPOCH_MAX && ssw_blk[threadIdx.x] != 0.f) atomicAdd(&w.ss[threadIdx.x], (double)ssw_blk[threadIdx.x]);
 }
 
 // any K (incl. the scalar first-order table, K = 1): one thread per (row, k)
@@ -554,6 +582,10 @@ static int launch_epoch_rows(int opt, int apply, float* var, float* slot0, float
   return CTR_OK;
 }
 
+static bool epoch_rows2_supported(int K) {
+  return K == 4 || K == 8 || K == 16 || K == 32 || K == 64 || K == 128 || K == 256;
+}
+
 static bool epoch_rows_supported(int K) {
   return K == 4 || K == 8 || K == 16 || K == 32 || K == 64 || K == 128 || K == 256 || (K >= 1 && K <= 256);
 }
@@ -571,6 +603,41 @@ int ctr_epoch_rows(int opt, int apply, float* var, float* slot0, float* slot1, u
   CTR_REQUIRE(epoch_rows_supported(K), CTR_ERR_UNSUPPORTED, "ctr_epoch_rows: K=%d must be <= 256", K);
   return launch_epoch_rows(opt, apply, var, slot0, slot1, last, uniq, n_uniq, g_uniq, n_max, K, hyper, lr_table, j,
                            ss, -1, as_stream(stream));
+}
+
+// The [N,K] table and a scalar table [N] gathered with the same ids (fm_v + fm_w), in ONE launch: lane 0 of every row
+// carries the scalar table's element.  Same arithmetic as two ctr_epoch_rows calls.
+int ctr_epoch_rows2(int opt, int apply, float* var, float* slot0, float* slot1, uint8_t* last, float* w_var, float* w_slot0,
+                    float* w_slot1, uint8_t* w_last, const int32_t* uniq, const int32_t* n_uniq, const float* g_uniq,
+                    const float* gw_uniq, int64_t n_max, int K, const float* hyper, const float* lr_table, int j, double* ss,
+                    double* ss_w, ctr_stream_t stream) {
+  CTR_REQUIRE(n_max >= 0 && j >= 0 && j < EPOCH_MAX, CTR_ERR_INVALID_ARG, "ctr_epoch_rows2: bad n_max/j");
+  CTR_REQUIRE(epoch_rows2_supported(K), CTR_ERR_UNSUPPORTED, "ctr_epoch_rows2: K=%d (supported: 4..256 powers of two)", K);
+  if (n_max == 0) return CTR_OK;
+  CTR_REQUIRE(var && slot0 && last && w_var && w_slot0 && w_last && uniq && n_uniq && hyper && lr_table && ss && ss_w,
+              CTR_ERR_INVALID_ARG, "ctr_epoch_rows2: null buffer");
+  CTR_REQUIRE(!apply || (g_uniq && gw_uniq), CTR_ERR_INVALID_ARG, "ctr_epoch_rows2: gradients required when apply != 0");
+  CTR_REQUIRE(n_slots_of(opt) == 1 || (slot1 && w_slot1), CTR_ERR_INVALID_ARG, "ctr_epoch_rows2: slot1 required");
+  cudaStream_t st = as_stream(stream);
+  RowsW w;
+  w.var = w_var; w.slot0 = w_slot0; w.slot1 = w_slot1; w.last = w_last; w.g_uniq = gw_uniq; w.ss = ss_w;
+#define ER2_K(OPT, AP, KK, LPR, VEC)                                                                       \
+  case KK:                                                                                                 \
+    epoch_rows_kernel<OPT, LPR, VEC, AP, true><<<(unsigned)ceil_div64(n_max * LPR, 256), 256, 0, st>>>(    \
+        var, slot0, slot1, last, uniq, n_uniq, g_uniq, n_max, hyper, lr_table, j, ss, -1, w);              \
+    break;
+#define ER2_AP(OPT, AP)                                                                                    \
+  switch (K) {                                                                                             \
+    ER2_K(OPT, AP, 4, 1, 1) ER2_K(OPT, AP, 8, 2, 1) ER2_K(OPT, AP, 16, 4, 1) ER2_K(OPT, AP, 32, 8, 1)      \
+    ER2_K(OPT, AP, 64, 16, 1) ER2_K(OPT, AP, 128, 32, 1) ER2_K(OPT, AP, 256, 32, 2)                        \
+  }
+#define ER2_CALL(OPT) if (apply) { ER2_AP(OPT, true) } else { ER2_AP(OPT, false) }
+  CTR_OPT_SWITCH(opt, ER2_CALL)
+#undef ER2_CALL
+#undef ER2_AP
+#undef ER2_K
+  CTR_LAUNCHED("ctr_epoch_rows2");
+  return CTR_OK;
 }
 
 int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* last, int64_t n_rows, int K,

@@ -155,6 +155,13 @@ class SparseUpdater:
         """tables_g: [(Table, g_uniq or None)].  apply=False: catch the gathered rows up to the start of
         step j; apply=True: take step j with the de-duplicated gradient."""
         o, uw = self.opt, self.uw
+        if (len(tables_g) == 2 and tables_g[0][0].K in ops.EPOCH_ROWS2_K and tables_g[1][0].K == 1
+                and tables_g[0][0].N == tables_g[1][0].N):
+            (V, gv), (W, gw) = tables_g            # fm_v + fm_w: one launch for both tables
+            ev, ew = self.ep[V.name], self.ep[W.name]
+            ops.epoch_rows2(o.opt, apply, V, W, ev["last"], ew["last"], uw.uniq, uw.n_uniq, gv if apply else None,
+                            gw if apply else None, self.n, o.record(HYPER_TABLE), o.lr_table, j, ev["ss"], ew["ss"])
+            return
         for t, g in tables_g:
             e = self.ep[t.name]
             ops.epoch_rows(o.opt, apply, t.var, t.slot(0), t.slot(1), e["last"], uw.uniq, uw.n_uniq,

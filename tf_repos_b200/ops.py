@@ -401,6 +401,22 @@ def epoch_rows(opt, apply: bool, var, slot0, slot1, last, uniq, n_uniq, g_uniq, 
         "ctr_epoch_rows")
 
 
+def epoch_rows2(opt, apply: bool, V, W, last_v, last_w, uniq, n_uniq, g_uniq, gw_uniq, n_max, hyper, lr_table, j, ss_v, ss_w):
+    """V / W: engine.Table ([N,K] and [N]) gathered with the same ids; one launch for both."""
+    f = torch.float32
+    check(
+        _L.ctr_epoch_rows2(
+            opt, int(apply), _p(V.var, f, "var"), _p(V.slot(0), f), _p(V.slot(1), f), _p(last_v, torch.uint8, "last"),
+            _p(W.var, f, "w_var"), _p(W.slot(0), f), _p(W.slot(1), f), _p(last_w, torch.uint8, "w_last"),
+            _p(uniq, torch.int32, "uniq"), _p(n_uniq, torch.int32, "n_uniq"), _p(g_uniq, f, "g_uniq"),
+            _p(gw_uniq, f, "gw_uniq"), n_max, V.K, _p(hyper, f, "hyper"), _p(lr_table, f, "lr_table"), j,
+            _p(ss_v, torch.float64, "ss"), _p(ss_w, torch.float64, "ss_w"), _stream()),
+        "ctr_epoch_rows2")
+
+
+EPOCH_ROWS2_K = (4, 8, 16, 32, 64, 128, 256)
+
+
 def epoch_partials_count() -> int:
     return int(_L.ctr_device_sm_count()) * 6
 
