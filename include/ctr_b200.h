@@ -109,7 +109,9 @@ int ctr_unique_segment(const int32_t* ids, int64_t n, int64_t N, int32_t* perm, 
 int ctr_segment_sum_rows(const float* g_rows, const float* g_w, const int32_t* perm,
                          const int32_t* seg_offsets, const int32_t* n_uniq,
                          const int32_t* long_list, int64_t n, int K, float* g_uniq, float* gw_uniq,
-                         ctr_stream_t stream);
+                         void* ws /* optional scratch (e.g. the ctr_unique_segment workspace, free by now): with
+                         >= (n/129+1)*16*(K+4)*4 bytes the long runs are split over 16 CTAs each; NULL = one CTA per run */,
+                         size_t ws_bytes, ctr_stream_t stream);
 
 /* ---- K4: optimizer apply on table rows ---------------------------------------------------------
  * TF-1.x arithmetic, [TF-sem] (see oracle/tf_semantics.py for the restatement and its sources).

@@ -40,7 +40,7 @@ SIGNATURES = {
     "ctr_fm_embed_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P]),
     "ctr_unique_segment_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "ctr_unique_segment": (c_int, [P, c_int64, c_int64, P, P, P, P, P, P, P, c_size_t, P]),
-    "ctr_segment_sum_rows": (c_int, [P, P, P, P, P, P, c_int64, c_int, P, P, P]),
+    "ctr_segment_sum_rows": (c_int, [P, P, P, P, P, P, c_int64, c_int, P, P, P, c_size_t, P]),
     "ctr_opt_sparse_rows": (c_int, [c_int, P, P, P, P, P, P, c_int64, c_int, P, P, P]),
     "ctr_opt_dense_sweep": (c_int, [c_int, P, P, P, c_int64, P, P, ctypes.POINTER(c_int), P]),
     "ctr_opt_patch_rows": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, P]),

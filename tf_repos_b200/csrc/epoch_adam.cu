@@ -99,7 +99,9 @@ __device__ __forceinline__ int pk_guess(const float2 (&x)[NP], const float2 (&m)
 }
 
 // ---- K % 4 == 0: a row is K/4 consecutive float4 ------------------------------------------------------------
-template <int MINB>
+// PREFETCH: the next grid-stride iteration's 6 float4 + `last` bytes are requested before this iteration's step loop
+// (26 more live registers: use with MINB = 2), so no warp waits on HBM between iterations.
+template <int MINB, bool PREFETCH = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, MINB)
 epoch_sweep_adam_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
                         const uint8_t* __restrict__ last, int64_t n4, int f4_per_row, int sh,
@@ -126,7 +128,24 @@ epoch_sweep_adam_kernel(float* __restrict__ var, float* __restrict__ slot0, floa
   float4* a4 = reinterpret_cast<float4*>(slot0);
   float4* b4 = reinterpret_cast<float4*>(slot1);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
+  struct Raw { float4 X[U], M[U], V[U]; int l0[U]; };
+  auto load_raw = [&](int64_t j0, Raw& r) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = j0 + u * stride;
+      r.l0[u] = -1;                                  // out of range
+      if (i < n4) {
+        r.X[u] = ld_stream4(v4 + i); r.M[u] = ld_stream4(a4 + i); r.V[u] = ld_stream4(b4 + i);
+        r.l0[u] = last[sh >= 0 ? (i >> sh) : (i / f4_per_row)];
+      }
+    }
+  };
+  Raw cur, nxt;
+  const int64_t i_first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (PREFETCH && i_first < n4) load_raw(i_first, cur);
+  for (int64_t i0 = i_first; i0 < n4; i0 += U * stride) {
+    if (!PREFETCH) load_raw(i0, cur);
+    else if (i0 + U * stride < n4) load_raw(i0 + U * stride, nxt);
     float2 x[NP], m[NP], v[NP];
     bool act[U];
     int nact = 0;
@@ -134,13 +153,12 @@ epoch_sweep_adam_kernel(float* __restrict__ var, float* __restrict__ slot0, floa
     for (int u = 0; u < U; ++u) {
       const int64_t i = i0 + u * stride;
       act[u] = false;
-      if (i < n4) {
-        const float4 X = ld_stream4(v4 + i), M = ld_stream4(a4 + i), V = ld_stream4(b4 + i);
-        x[2 * u] = make_float2(X.x, X.y); x[2 * u + 1] = make_float2(X.z, X.w);
-        m[2 * u] = make_float2(M.x, M.y); m[2 * u + 1] = make_float2(M.z, M.w);
-        v[2 * u] = make_float2(V.x, V.y); v[2 * u + 1] = make_float2(V.z, V.w);
+      if (cur.l0[u] >= 0) {
+        x[2 * u] = make_float2(cur.X[u].x, cur.X[u].y); x[2 * u + 1] = make_float2(cur.X[u].z, cur.X[u].w);
+        m[2 * u] = make_float2(cur.M[u].x, cur.M[u].y); m[2 * u + 1] = make_float2(cur.M[u].z, cur.M[u].w);
+        v[2 * u] = make_float2(cur.V[u].x, cur.V[u].y); v[2 * u + 1] = make_float2(cur.V[u].z, cur.V[u].w);
         const int64_t row = sh >= 0 ? (i >> sh) : (i / f4_per_row);
-        const int l0 = last[row];
+        const int l0 = cur.l0[u];
         act[u] = l0 == from;
         if (l0 > from && row * f4_per_row == i) {   // gathered since `from`: second pass (head lane appends)
           const int pos = atomicAdd(list_count, 1);
@@ -149,6 +167,7 @@ epoch_sweep_adam_kernel(float* __restrict__ var, float* __restrict__ slot0, floa
       }
       nact += act[u] ? 1 : 0;
     }
+    if (PREFETCH) cur = nxt;
     if (nact == 0) continue;
     if (!act[0]) { x[0] = x[2]; x[1] = x[3]; m[0] = m[2]; m[1] = m[3]; v[0] = v[2]; v[1] = v[3]; }
     if (!act[1]) { x[2] = x[0]; x[3] = x[1]; m[2] = m[0]; m[3] = m[1]; v[2] = v[0]; v[3] = v[1]; }
@@ -457,12 +476,26 @@ static void launch_sweep_minb(float* var, float* slot0, float* slot1, const uint
   }
   const float nz = -0.0f;
   const int grid = sm_count() * MINB;
+  static int pf = -1;
+  if (pf < 0) { const char* e = getenv("CTR_SWEEP_PF"); pf = e ? atoi(e) : 1; }
   if (K % 4 == 0) {
     const int f4 = K / 4;
     const int sh = (f4 & (f4 - 1)) == 0 ? (31 - __builtin_clz((unsigned)f4)) : -1;
-    epoch_sweep_adam_kernel<MINB><<<grid, SWEEP_THREADS, smem, st>>>(var, slot0, slot1, last, n_rows * f4, f4, sh, hyper,
-                                                                     lr_table, from, upto, ss_partials, n_partials, list,
-                                                                     list_count, list_cap, nz);
+    if (pf) {
+      static bool attr_pf = false;
+      if (!attr_pf) {
+        cudaFuncSetAttribute(epoch_sweep_adam_kernel<MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (EPOCH_MAX_A + 2 * EPOCH_MAX_A * SWEEP_THREADS) * (int)sizeof(float));
+        attr_pf = true;
+      }
+      epoch_sweep_adam_kernel<MINB, true><<<grid, SWEEP_THREADS, smem, st>>>(var, slot0, slot1, last, n_rows * f4, f4, sh,
+                                                                             hyper, lr_table, from, upto, ss_partials,
+                                                                             n_partials, list, list_count, list_cap, nz);
+    } else {
+      epoch_sweep_adam_kernel<MINB><<<grid, SWEEP_THREADS, smem, st>>>(var, slot0, slot1, last, n_rows * f4, f4, sh, hyper,
+                                                                       lr_table, from, upto, ss_partials, n_partials, list,
+                                                                       list_count, list_cap, nz);
+    }
   } else {
     epoch_sweep_adam_k1_kernel<MINB><<<grid, SWEEP_THREADS, smem, st>>>(var, slot0, slot1, last, n_rows / 4, hyper,
                                                                         lr_table, from, upto, ss_partials, n_partials,
@@ -479,8 +512,8 @@ bool launch_epoch_sweep_adam(float* var, float* slot0, float* slot1, const uint8
   static int minb = 0;
   if (!minb) {
     const char* e = getenv("CTR_SWEEP_MINB");
-    minb = e ? atoi(e) : 3;
-    if (minb < 2 || minb > 4) minb = 3;
+    minb = e ? atoi(e) : 2;   // measured (profiles/r02_time_sweep_pf.txt): 2 CTAs/SM + register prefetch 44.4 ms, 3 CTAs/SM 48.0 ms
+    if (minb < 2 || minb > 4) minb = 2;
   }
 #define SW_ARGS var, slot0, slot1, last, n_rows, K, hyper, lr_table, from, upto, ss_partials, n_partials, list, list_count, list_cap, st
   if (minb == 2) launch_sweep_minb<2>(SW_ARGS);

@@ -135,6 +135,79 @@ segsum_long_kernel(const float* __restrict__ g_rows, const float* __restrict__ g
   }
 }
 
+// Long runs split over SPLIT CTAs each (13 runs of B occurrences keep 13 CTAs busy otherwise): chunk c of run li sums
+// occurrences [c*len/SPLIT, (c+1)*len/SPLIT) with the same lane-group striding + fixed tree and writes a partial row;
+// segsum_long_final_kernel adds the SPLIT partials in chunk order.  Fixed shape => bit-reproducible.
+constexpr int SEG_SPLIT = 16;
+
+template <int LPR, int VEC>
+__global__ void __launch_bounds__(256)
+segsum_long_split_kernel(const float* __restrict__ g_rows, const float* __restrict__ g_w,
+                         const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_offsets,
+                         const int32_t* __restrict__ long_list, int max_long, float* __restrict__ partial) {
+  constexpr int K = 4 * LPR * VEC;
+  constexpr int G = 256 / LPR;
+  __shared__ float4 sm[VEC][256];
+  __shared__ float smw[G];
+  const int g = threadIdx.x / LPR, c = threadIdx.x % LPR;
+  const int n_long = min(long_list[0], max_long);
+  const int chunk = blockIdx.x;
+  for (int li = blockIdx.y; li < n_long; li += gridDim.y) {
+    const int u = long_list[1 + li];
+    const int start0 = seg_offsets[u];
+    const int len0 = seg_offsets[u + 1] - start0;
+    const int lo = (int)((int64_t)len0 * chunk / SEG_SPLIT), hi = (int)((int64_t)len0 * (chunk + 1) / SEG_SPLIT);
+    const int start = start0 + lo, len = hi - lo;
+    float4 acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
+    float accw = 0.f;
+    for (int i = g; i < len; i += G) {
+      const int32_t p = perm[start + i];
+      const float4* row = reinterpret_cast<const float4*>(g_rows + (int64_t)p * K) + c;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = f4_add(acc[v], row[v * LPR]);
+      if (g_w && c == 0) accw += g_w[p];
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) sm[v][threadIdx.x] = acc[v];
+    if (c == 0) smw[g] = accw;
+    __syncthreads();
+    for (int half = G / 2; half > 0; half >>= 1) {
+      if (g < half) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          sm[v][threadIdx.x] = f4_add(sm[v][threadIdx.x], sm[v][threadIdx.x + half * LPR]);
+        if (c == 0) smw[g] += smw[g + half];
+      }
+      __syncthreads();
+    }
+    if (g == 0) {
+      float* prow = partial + ((int64_t)li * SEG_SPLIT + chunk) * (K + 4);
+      float4* o = reinterpret_cast<float4*>(prow) + c;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o[v * LPR] = sm[v][threadIdx.x];
+      if (c == 0) prow[K] = smw[0];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void segsum_long_final_kernel(const float* __restrict__ partial, const int32_t* __restrict__ long_list,
+                                         int max_long, int K, float* __restrict__ g_uniq, float* __restrict__ gw_uniq) {
+  const int n_long = min(long_list[0], max_long);
+  for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
+    const int u = long_list[1 + li];
+    for (int k = threadIdx.x; k <= K; k += blockDim.x) {
+      if (k == K && !gw_uniq) continue;
+      float s = 0.f;
+      for (int ch = 0; ch < SEG_SPLIT; ++ch) s += partial[((int64_t)li * SEG_SPLIT + ch) * (K + 4) + k];
+      if (k < K) g_uniq[(int64_t)u * K + k] = s;
+      else gw_uniq[u] = s;
+    }
+  }
+}
+
 // any K: one warp per run, lanes stride k.  (long runs are summed sequentially here.)
 __global__ void __launch_bounds__(256)
 segsum_generic_kernel(const float* __restrict__ g_rows, const float* __restrict__ g_w,
@@ -165,7 +238,7 @@ using namespace ctr;
 extern "C" int ctr_segment_sum_rows(const float* g_rows, const float* g_w, const int32_t* perm,
                                     const int32_t* seg_offsets, const int32_t* n_uniq,
                                     const int32_t* long_list, int64_t n, int K, float* g_uniq,
-                                    float* gw_uniq, ctr_stream_t stream) {
+                                    float* gw_uniq, void* ws, size_t ws_bytes, ctr_stream_t stream) {
   CTR_REQUIRE(n >= 0 && K > 0, CTR_ERR_INVALID_ARG, "ctr_segment_sum_rows: bad n/K");
   if (n == 0) return CTR_OK;
   CTR_REQUIRE(g_rows && perm && seg_offsets && n_uniq && long_list && g_uniq, CTR_ERR_INVALID_ARG,
@@ -174,15 +247,29 @@ extern "C" int ctr_segment_sum_rows(const float* g_rows, const float* g_w, const
               "ctr_segment_sum_rows: g_w and gw_uniq must both be given or both be NULL");
   cudaStream_t st = as_stream(stream);
   const int long_grid = 2 * sm_count();
+  // optional scratch (the K3 workspace is free by now): long runs split over SEG_SPLIT CTAs each
+  const int64_t max_long_possible = n / (CTR_LONG_SEG + 1) + 1;
+  const size_t split_need = (size_t)max_long_possible * SEG_SPLIT * (size_t)(K + 4) * sizeof(float);
+  const bool split = ws && ws_bytes >= split_need && ((uintptr_t)ws & 15) == 0;
+  float* partial = reinterpret_cast<float*>(ws);
 #define SEG_CASE(KK, LPR, VEC)                                                                      \
   case KK: {                                                                                        \
     unsigned blocks = (unsigned)ceil_div64(n * LPR, 256);                                           \
     segsum_short_kernel<LPR, VEC><<<blocks, 256, 0, st>>>(g_rows, g_w, perm, seg_offsets, n_uniq,   \
                                                           n, g_uniq, gw_uniq);                      \
     CTR_LAUNCHED("segsum_short");                                                                   \
-    segsum_long_kernel<LPR, VEC><<<long_grid, 256, 0, st>>>(g_rows, g_w, perm, seg_offsets,         \
-                                                            long_list, g_uniq, gw_uniq);            \
-    CTR_LAUNCHED("segsum_long");                                                                    \
+    if (split) {                                                                                    \
+      segsum_long_split_kernel<LPR, VEC><<<dim3(SEG_SPLIT, 32), 256, 0, st>>>(                      \
+          g_rows, g_w, perm, seg_offsets, long_list, (int)max_long_possible, partial);              \
+      CTR_LAUNCHED("segsum_long_split");                                                            \
+      segsum_long_final_kernel<<<64, 128, 0, st>>>(partial, long_list, (int)max_long_possible, K,   \
+                                                   g_uniq, gw_uniq);                                \
+      CTR_LAUNCHED("segsum_long_final");                                                            \
+    } else {                                                                                        \
+      segsum_long_kernel<LPR, VEC><<<long_grid, 256, 0, st>>>(g_rows, g_w, perm, seg_offsets,       \
+                                                              long_list, g_uniq, gw_uniq);          \
+      CTR_LAUNCHED("segsum_long");                                                                  \
+    }                                                                                               \
     break;                                                                                          \
   }
   switch (K) {

@@ -105,7 +105,8 @@ def segment_sum_rows(g_rows, g_w, uw: UniqueWorkspace, K, g_uniq, gw_uniq=None):
         _L.ctr_segment_sum_rows(
             _p(g_rows, torch.float32, "g_rows"), _p(g_w, torch.float32, "g_w"), _p(uw.perm),
             _p(uw.seg_offsets), _p(uw.n_uniq), _p(uw.long_list), getattr(uw, "n_active", uw.n), K,
-            _p(g_uniq, torch.float32, "g_uniq"), _p(gw_uniq, torch.float32, "gw_uniq"), _stream()),
+            _p(g_uniq, torch.float32, "g_uniq"), _p(gw_uniq, torch.float32, "gw_uniq"), _p(uw.ws), uw.ws.numel(),
+            _stream()),
         "ctr_segment_sum_rows")
 
 

@@ -2,9 +2,11 @@
 # north_star: an ncu capture (--set full) for every hand-written kernel of the hot path; summaries -> profiles/
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out/ncu
-NCU="ncu --profile-from-start off --set full --clock-control none --import-source on -f"
+NCU="ncu --profile-from-start off --set full --clock-control none -f"
 run() { # name regex count model
-  timeout -k 5 400 $NCU -k "regex:$2" -c $3 -o gpurun_out/ncu/r02_$1 python tools/profile_step.py $4 > gpurun_out/ncu/r02_$1.log 2>&1; echo "$1 rc=$?"
+  timeout -k 5 400 $NCU -k "regex:$2" -c $3 -o /tmp/r02_$1 python tools/profile_step.py $4 > gpurun_out/ncu/r02_$1.log 2>&1; echo "$1 rc=$?"
+  # only the text summary travels back (gpurun_out is capped at 64 MiB; a --set full report is 1-2 MB per launch)
+  python tools/ncu_summary.py /tmp/r02_$1.ncu-rep gpurun_out/ncu/r02_ncu_$1.txt > /dev/null 2>&1; rm -f /tmp/r02_$1.ncu-rep
 }
 run deepfm_step "fm_embed|segsum|radix|heads_|long_list|epoch_rows|tc_gemm|fc_dz|fc1_|logit_loss|dropout_mask|opt_dense_grad|splitk|epoch_tick" 60 deepfm
 run dcn_cross "cross_" 4 dcn
