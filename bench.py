@@ -522,7 +522,7 @@ def main_b200(args):
                     "sweep_avg_ms": (sum(e2e_sweep_ms) / len(e2e_sweep_ms) if e2e_sweep_ms else None),
                     "clocks": sampler2.summary()},
             "gpu_launches": launches, "clocks": sampler.summary(),
-            "roofline": {"kernel": f"epoch_sweep_kernel<ADAM> on fm_v ({EPOCH} Adam steps per element per pass)",
+            "roofline": {"kernel": f"epoch_sweep_adam_kernel on fm_v ({EPOCH} Adam steps per element per pass; CUDA events around the pass incl. the ~1 ms second pass over the rows gathered during the epoch)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak if achieved else None), "traffic": traffic,
                          "algorithmic_bytes_per_launch": table_bytes, "avg_launch_ms": sweep_avg_ms,
@@ -535,14 +535,15 @@ def main_b200(args):
                          # would have to deliver to match this launch -- context, not the roofline fraction
                          "per_step_formulation_equiv_GBps": (EPOCH * achieved if achieved else None),
                          "issue_active_pct_ncu": issue_pct,
-                         "note": "by design NOT HBM-bound: the kernel replays 16 optimizer steps per element in "
-                                 "registers (IEEE div+sqrt recurrence, 29.5 instr/element/step against an arithmetic "
-                                 "floor of 24) to cut HBM traffic 16x; its limiter is instruction issue (77 % "
-                                 "issue-active, profiles/r01_ncu_epoch_sweep_full.txt).  The HBM-bound formulation "
-                                 "of the same update is reported under exact_every_step.  The grouped IEEE fast path is valid "
-                                 "while |lr_t*m| >= 2^-100, i.e. for about the first 650 steps of a run with these "
-                                 "defaults (the timed steps are inside that window); later steps fall back to the "
-                                 "compiler's per-element div/sqrt (sweep ~1.3x slower), see DESIGN.md section 6."}}
+                         "fma_pipe_active_pct_ncu": (json.load(open(os.path.join(ROOT, "profiles", "sweep_traffic.json"))).get("epoch_fma_pipe_active_pct") if os.path.exists(os.path.join(ROOT, "profiles", "sweep_traffic.json")) else None),
+                         "note": "by design NOT HBM-bound: the pass replays 16 optimizer steps per element in registers (IEEE "
+                                 "div+sqrt recurrence: 21 fp32 operations + 2 MUFU per element-step, bit-identical to the every-step "
+                                 "formulation) to cut HBM traffic 16x; its limiter is instruction issue on the packed fp32 pipe "
+                                 "(FFMA2-class instructions hold the port 2 cycles: profiles/r02_ubench_f32x2.txt, "
+                                 "profiles/r02_ncu_sweep_adam_packed.txt).  `frac` is computed from full 16-step passes only; the "
+                                 "flush that ends the timed region is listed under partial_passes.  The HBM-bound formulation of the "
+                                 "same update is reported under exact_every_step; the same steps from the long-run (parked) table "
+                                 "state under steady_state."}}
     if exact_sweep_ms:
         ex_avg = sum(exact_sweep_ms) / len(exact_sweep_ms)
         tr = None

@@ -231,7 +231,7 @@ epoch_sweep_adam_kernel(float* __restrict__ var, float* __restrict__ slot0, floa
 }
 
 // ---- K == 1 (first-order weights): a float4 holds 4 rows, each with its own `last` byte ------------------------
-template <int MINB>
+template <int MINB, bool PREFETCH = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, MINB)
 epoch_sweep_adam_k1_kernel(float* __restrict__ var, float* __restrict__ slot0, float* __restrict__ slot1,
                            const uint8_t* __restrict__ last, int64_t n4, const float* __restrict__ hyper,
@@ -258,41 +258,55 @@ epoch_sweep_adam_k1_kernel(float* __restrict__ var, float* __restrict__ slot0, f
   float4* b4 = reinterpret_cast<float4*>(slot1);
   const uint32_t* l4 = reinterpret_cast<const uint32_t*>(last);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
+  struct Raw { float4 X[U], M[U], V[U]; uint32_t lw[U]; bool in[U]; };
+  auto load_raw = [&](int64_t j0, Raw& r) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = j0 + u * stride;
+      r.in[u] = i < n4;
+      r.lw[u] = 0xffffffffu;
+      if (r.in[u]) { r.X[u] = ld_stream4(v4 + i); r.M[u] = ld_stream4(a4 + i); r.V[u] = ld_stream4(b4 + i); r.lw[u] = l4[i]; }
+      else { r.X[u] = r.M[u] = r.V[u] = f4_zero(); }
+    }
+  };
+  Raw cur, nxt;
+  const int64_t i_first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (PREFETCH && i_first < n4) load_raw(i_first, cur);
+  for (int64_t i0 = i_first; i0 < n4; i0 += U * stride) {
+    if (!PREFETCH) load_raw(i0, cur);
+    else if (i0 + U * stride < n4) load_raw(i0 + U * stride, nxt);
     float xe[NE], me[NE], ve[NE];
-    bool act[NE];
-    int nact = 0, donor = -1;
+    unsigned actm = 0;            // bit e: element e replays from..upto-1 here
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t i = i0 + u * stride;
-      uint32_t lw = 0xffffffffu;   // out of bounds: every byte 255 >= upto
-      float4 X = f4_zero(), M = f4_zero(), V = f4_zero();
-      if (i < n4) { X = ld_stream4(v4 + i); M = ld_stream4(a4 + i); V = ld_stream4(b4 + i); lw = l4[i]; }
-      xe[4 * u] = X.x; xe[4 * u + 1] = X.y; xe[4 * u + 2] = X.z; xe[4 * u + 3] = X.w;
-      me[4 * u] = M.x; me[4 * u + 1] = M.y; me[4 * u + 2] = M.z; me[4 * u + 3] = M.w;
-      ve[4 * u] = V.x; ve[4 * u + 1] = V.y; ve[4 * u + 2] = V.z; ve[4 * u + 3] = V.w;
+      xe[4 * u] = cur.X[u].x; xe[4 * u + 1] = cur.X[u].y; xe[4 * u + 2] = cur.X[u].z; xe[4 * u + 3] = cur.X[u].w;
+      me[4 * u] = cur.M[u].x; me[4 * u + 1] = cur.M[u].y; me[4 * u + 2] = cur.M[u].z; me[4 * u + 3] = cur.M[u].w;
+      ve[4 * u] = cur.V[u].x; ve[4 * u + 1] = cur.V[u].y; ve[4 * u + 2] = cur.V[u].z; ve[4 * u + 3] = cur.V[u].w;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int l0 = (int)((lw >> (8 * e)) & 255u);
-        act[4 * u + e] = i < n4 && l0 == from;
-        if (i < n4 && l0 > from) {
+        const int l0 = (int)((cur.lw[u] >> (8 * e)) & 255u);
+        if (cur.in[u] && l0 == from) actm |= 1u << (4 * u + e);
+        if (cur.in[u] && l0 > from) {      // gathered since `from`: second pass
           const int pos = atomicAdd(list_count, 1);
           if (pos < list_cap) list[pos] = (int32_t)(4 * i + e);
         }
-        if (act[4 * u + e]) { ++nact; if (donor < 0) donor = 4 * u + e; }
       }
     }
-    if (nact == 0) continue;
+    if (PREFETCH) cur = nxt;
+    if (actm == 0) continue;
+    // donor for the inactive slots: the first active element (chained selects, highest index first)
     float xd = 0.f, md = 0.f, vd = 0.f;
 #pragma unroll
-    for (int e = 0; e < NE; ++e) if (e == donor) { xd = xe[e]; md = me[e]; vd = ve[e]; }
+    for (int e = NE - 1; e >= 0; --e) if (actm & (1u << e)) { xd = xe[e]; md = me[e]; vd = ve[e]; }
     float2 x[NP], m[NP], v[NP], w[NP];
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-      w[p] = make_float2(act[2 * p] ? 1.f : 0.f, act[2 * p + 1] ? 1.f : 0.f);   // dummy slots do not count in sum(var^2)
-      x[p] = make_float2(act[2 * p] ? xe[2 * p] : xd, act[2 * p + 1] ? xe[2 * p + 1] : xd);
-      m[p] = make_float2(act[2 * p] ? me[2 * p] : md, act[2 * p + 1] ? me[2 * p + 1] : md);
-      v[p] = make_float2(act[2 * p] ? ve[2 * p] : vd, act[2 * p + 1] ? ve[2 * p + 1] : vd);
+      const bool a0 = actm & (1u << (2 * p)), a1 = actm & (1u << (2 * p + 1));
+      w[p] = make_float2(a0 ? 1.f : 0.f, a1 ? 1.f : 0.f);   // dummy slots do not count in sum(var^2)
+      x[p] = make_float2(a0 ? xe[2 * p] : xd, a1 ? xe[2 * p + 1] : xd);
+      m[p] = make_float2(a0 ? me[2 * p] : md, a1 ? me[2 * p + 1] : md);
+      v[p] = make_float2(a0 ? ve[2 * p] : vd, a1 ? ve[2 * p + 1] : vd);
     }
     const int mode = pk_guess<NP>(x, m, v, c, lr0, okA, okS);
     bool done = false;
@@ -303,8 +317,18 @@ epoch_sweep_adam_k1_kernel(float* __restrict__ var, float* __restrict__ slot0, f
       for (int s = 0; s < nsteps; ++s)
         sm.ss_thr[s * SWEEP_THREADS + threadIdx.x] += sm.ss_tmp[s * SWEEP_THREADS + threadIdx.x];
     } else {
-      // rare (a trajectory outside the exact range): scalar replay of the active elements from the loaded state,
+      // rare (a trajectory outside the exact range): scalar replay of the active elements from the STORED state,
       // IEEE sqrt/div from the compiler
+      float ye[NE], ne[NE], ue[NE];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        float4 X = f4_zero(), M = f4_zero(), V = f4_zero();
+        if (i < n4) { X = ld_stream4(v4 + i); M = ld_stream4(a4 + i); V = ld_stream4(b4 + i); }
+        ye[4 * u] = X.x; ye[4 * u + 1] = X.y; ye[4 * u + 2] = X.z; ye[4 * u + 3] = X.w;
+        ne[4 * u] = M.x; ne[4 * u + 1] = M.y; ne[4 * u + 2] = M.z; ne[4 * u + 3] = M.w;
+        ue[4 * u] = V.x; ue[4 * u + 1] = V.y; ue[4 * u + 2] = V.z; ue[4 * u + 3] = V.w;
+      }
       Hyper h = h0;
 #pragma unroll 1
       for (int s = from; s < upto; ++s) {
@@ -312,32 +336,33 @@ epoch_sweep_adam_k1_kernel(float* __restrict__ var, float* __restrict__ slot0, f
         float q = 0.f;
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
-          if (act[e]) { q += xe[e] * xe[e]; step_sparse<CTR_OPT_ADAM>(xe[e], me[e], ve[e], __fmul_rn(h.l2, xe[e]), h); }
+          if (actm & (1u << e)) { q += ye[e] * ye[e]; step_sparse<CTR_OPT_ADAM>(ye[e], ne[e], ue[e], __fmul_rn(h.l2, ye[e]), h); }
         }
         sm.ss_thr[(s - from) * SWEEP_THREADS + threadIdx.x] += q;
       }
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
-        x[p] = make_float2(xe[2 * p], xe[2 * p + 1]); m[p] = make_float2(me[2 * p], me[2 * p + 1]);
-        v[p] = make_float2(ve[2 * p], ve[2 * p + 1]);
+        x[p] = make_float2(ye[2 * p], ye[2 * p + 1]); m[p] = make_float2(ne[2 * p], ne[2 * p + 1]);
+        v[p] = make_float2(ue[2 * p], ue[2 * p + 1]);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t i = i0 + u * stride;
-      if (i < n4 && (act[4 * u] || act[4 * u + 1] || act[4 * u + 2] || act[4 * u + 3])) {
+      const unsigned am = (actm >> (4 * u)) & 15u;
+      if (am) {
         // inactive elements keep their stored value (the second pass owns them): element-wise stores
-        float* px = var + 4 * i; float* pm = slot0 + 4 * i; float* pv = slot1 + 4 * i;
         const float ox[4] = {x[2 * u].x, x[2 * u].y, x[2 * u + 1].x, x[2 * u + 1].y};
         const float om[4] = {m[2 * u].x, m[2 * u].y, m[2 * u + 1].x, m[2 * u + 1].y};
         const float ov[4] = {v[2 * u].x, v[2 * u].y, v[2 * u + 1].x, v[2 * u + 1].y};
-        if (act[4 * u] && act[4 * u + 1] && act[4 * u + 2] && act[4 * u + 3]) {
+        if (am == 15u) {
           st_stream4(v4 + i, make_float4(ox[0], ox[1], ox[2], ox[3]));
           st_stream4(a4 + i, make_float4(om[0], om[1], om[2], om[3]));
           st_stream4(b4 + i, make_float4(ov[0], ov[1], ov[2], ov[3]));
         } else {
+          float* px = var + 4 * i; float* pm = slot0 + 4 * i; float* pv = slot1 + 4 * i;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) if (act[4 * u + e]) { px[e] = ox[e]; pm[e] = om[e]; pv[e] = ov[e]; }
+          for (int e = 0; e < 4; ++e) if (am & (1u << e)) { px[e] = ox[e]; pm[e] = om[e]; pv[e] = ov[e]; }
         }
       }
     }
@@ -497,9 +522,21 @@ static void launch_sweep_minb(float* var, float* slot0, float* slot1, const uint
                                                                        list_count, list_cap, nz);
     }
   } else {
-    epoch_sweep_adam_k1_kernel<MINB><<<grid, SWEEP_THREADS, smem, st>>>(var, slot0, slot1, last, n_rows / 4, hyper,
-                                                                        lr_table, from, upto, ss_partials, n_partials,
-                                                                        list, list_count, list_cap, nz);
+    if (pf) {
+      static bool attr_pf1 = false;
+      if (!attr_pf1) {
+        cudaFuncSetAttribute(epoch_sweep_adam_k1_kernel<MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (EPOCH_MAX_A + 2 * EPOCH_MAX_A * SWEEP_THREADS) * (int)sizeof(float));
+        attr_pf1 = true;
+      }
+      epoch_sweep_adam_k1_kernel<MINB, true><<<grid, SWEEP_THREADS, smem, st>>>(var, slot0, slot1, last, n_rows / 4, hyper,
+                                                                                lr_table, from, upto, ss_partials,
+                                                                                n_partials, list, list_count, list_cap, nz);
+    } else {
+      epoch_sweep_adam_k1_kernel<MINB><<<grid, SWEEP_THREADS, smem, st>>>(var, slot0, slot1, last, n_rows / 4, hyper,
+                                                                          lr_table, from, upto, ss_partials, n_partials,
+                                                                          list, list_count, list_cap, nz);
+    }
   }
 }
 
