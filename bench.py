@@ -581,11 +581,14 @@ def side_models(torch, dev, synth, vocab):
     inputs resident in HBM, CUDA-event timed over one epoch of 16 steps + the closing sweep."""
     out = {}
 
-    def timeit(step, m, steps):
+    def timeit(step, m, steps, graphed=False):
         for i in range(3):
             step(i)
         while m.epoch_pos != 0:
             step(0)
+        if graphed:      # a position's first visit is eager, its second visit captures the CUDA graph: both are warm-up
+            for i in range(2 * EPOCH):
+                step(i)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -601,7 +604,7 @@ def side_models(torch, dev, synth, vocab):
         B, F, K, L = 8192, 39, 16, 6
         bt = [synth.criteo_batch(B, vocab, F, seed=50 + i, device=dev) for i in range(8)]
         m = DCN(F, vocab, K, B, cross_layers=L, update_mode="exact_deferred", epoch_steps=EPOCH, device=dev)
-        ms = timeit(lambda i: m.train_step_graphed(*bt[i % 8]), m, 2 * EPOCH)
+        ms = timeit(lambda i: m.train_step_graphed(*bt[i % 8]), m, 2 * EPOCH, graphed=True)
         out["configs[2]_dcn"] = {"value": B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms,
                                  "config": f"DCN 1xB200, B={B} F={F} vocab={vocab} k={K} cross_layers={L}, Adam, l2 1e-4, "
                                            "dropout 0.5, exact TF update semantics (exact-deferred)"}

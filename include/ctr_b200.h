@@ -109,8 +109,9 @@ int ctr_unique_segment(const int32_t* ids, int64_t n, int64_t N, int32_t* perm, 
 int ctr_segment_sum_rows(const float* g_rows, const float* g_w, const int32_t* perm,
                          const int32_t* seg_offsets, const int32_t* n_uniq,
                          const int32_t* long_list, int64_t n, int K, float* g_uniq, float* gw_uniq,
-                         void* ws /* optional scratch (e.g. the ctr_unique_segment workspace, free by now): with
-                         >= (n/129+1)*16*(K+4)*4 bytes the long runs are split over 16 CTAs each; NULL = one CTA per run */,
+                         void* ws /* optional scratch (e.g. the ctr_unique_segment workspace, free by now): runs longer than
+                         CTR_LONG_SEG are cut into 1024-occurrence chunks summed by separate CTAs and added in chunk order
+                         (as many runs as the scratch has partial rows for); NULL = one CTA per long run */,
                          size_t ws_bytes, ctr_stream_t stream);
 
 /* ---- K4: optimizer apply on table rows ---------------------------------------------------------
@@ -258,12 +259,13 @@ int ctr_dropout_mask(float* mask, int64_t n, float keep_prob, uint64_t seed, con
  * train != 0: batch moments (biased variance) -> save_mean / save_var [H]; moving_mean / moving_var are updated in
  * place (moving -= (moving - batch)*(1 - decay)).  train == 0: moving statistics, no dropout, nothing written but out.
  * ctr_bn_bwd: gradients through the batch moments; d_x [n,H], d_gamma / d_beta [H] (overwritten). */
+size_t ctr_bn_workspace_bytes(int H);   /* scratch for the chunked column reductions (TRAIN forward and backward) */
 int ctr_bn_fwd(const float* x, int n, int H, const float* gamma, const float* beta, float* moving_mean,
                float* moving_var, int train, float decay, float eps, const float* drop_mask, float keep_prob, float* out,
-               float* save_mean, float* save_var, ctr_stream_t stream);
+               float* save_mean, float* save_var, void* ws, size_t ws_bytes, ctr_stream_t stream);
 int ctr_bn_bwd(const float* d_out, const float* x, int n, int H, const float* save_mean, const float* save_var,
                const float* gamma, float eps, const float* drop_mask, float keep_prob, float* d_x, float* d_gamma,
-               float* d_beta, ctr_stream_t stream);
+               float* d_beta, void* ws, size_t ws_bytes, ctr_stream_t stream);
 
 /* ---- K5: DCN cross network (DCN.py:140-145) ------------------------------------------------------
  * x_{l+1} = x0 * (x_l . w_l) + x_l + b_l,  l = 0..L-1;  w,b: [L,D];  x0: [B,D], D = F*K (D%4==0, <=2048)

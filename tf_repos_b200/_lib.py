@@ -67,8 +67,9 @@ SIGNATURES = {
     "ctr_fc1_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ctr_fc1_bwd": (c_int, [P, c_int, P, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
     "ctr_dropout_mask": (c_int, [P, c_int64, c_float, c_uint64, P, P]),
-    "ctr_bn_fwd": (c_int, [P, c_int, c_int, P, P, P, P, c_int, c_float, c_float, P, c_float, P, P, P, P]),
-    "ctr_bn_bwd": (c_int, [P, P, c_int, c_int, P, P, P, c_float, P, c_float, P, P, P, P]),
+    "ctr_bn_workspace_bytes": (c_size_t, [c_int]),
+    "ctr_bn_fwd": (c_int, [P, c_int, c_int, P, P, P, P, c_int, c_float, c_float, P, c_float, P, P, P, P, c_size_t, P]),
+    "ctr_bn_bwd": (c_int, [P, P, c_int, c_int, P, P, P, c_float, P, c_float, P, P, P, P, c_size_t, P]),
     "ctr_cross_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P]),
     "ctr_cross_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ctr_cross_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),

@@ -212,14 +212,23 @@ fc1_bwd_kernel(const float* __restrict__ in_a, int Ka, const float* __restrict__
   }
 }
 
-// partial rows are [dw(Kt) | db(1)]
-__global__ void fc1_reduce_kernel(const float* __restrict__ part, int chunks, int Kt, float* __restrict__ dw,
-                                  float* __restrict__ db) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > Kt) return;
+// out[k] = sum_c part[c*ld + k] for many partial rows (thousands when M = B*P): 32 columns x 8 row groups per CTA,
+// each group adds rows g, g+8, ... in order, then a fixed 8-way tree.  Columns [0, na) go to out_a, the rest to out_b.
+__global__ void __launch_bounds__(256)
+colsum_rows_kernel(const float* __restrict__ part, int chunks, int ld, int ncols, int na, float* __restrict__ out_a,
+                   float* __restrict__ out_b) {
+  __shared__ float red[8][33];
+  const int k = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
   float s = 0.f;
-  for (int c = 0; c < chunks; ++c) s += part[(int64_t)c * (Kt + 1) + k];
-  if (k < Kt) dw[k] = s; else db[0] = s;
+  if (k < ncols) for (int c = g; c < chunks; c += 8) s += part[(int64_t)c * ld + k];
+  red[g][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (g == 0 && k < ncols) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+    if (k < na) out_a[k] = t; else out_b[k - na] = t;
+  }
 }
 
 // binary keep mask (1.0 / 0.0) from a counter-based hash: tf.nn.dropout's floor(keep + U[0,1))
@@ -327,7 +336,7 @@ int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* 
   // 1. dZ in place + bias gradient
   fc_dz_kernel<<<dim3((Nd + 31) / 32, chunks), 256, 0, st>>>(dOut, out, drop_mask, keep_prob, M, Nd, act, colsum);
   CTR_LAUNCHED("fc_dz");
-  splitk_reduce_kernel<<<(Nd + 255) / 256, 256, 0, st>>>(colsum, chunks, Nd, db);
+  colsum_rows_kernel<<<(Nd + 31) / 32, 256, 0, st>>>(colsum, chunks, Nd, Nd, Nd, db, nullptr);
   CTR_LAUNCHED("fc_db_reduce");
   // 2. dW[Kd,Nd] = in^T @ dZ, split over M
   // narrow layer input (DIN attention: Kd = 32, Nd = 256, M = B*P = 409600): as in^T @ dZ the 128-row MMA tile
@@ -400,7 +409,7 @@ int ctr_fc1_bwd(const float* in_a, int Ka, const float* in_b, int Kb, const floa
   fc1_bwd_kernel<<<chunks, 256, 0, st>>>(in_a, Ka, in_b, Kb, w, dy, M, d_a, d_b, part);
   CTR_LAUNCHED("fc1_bwd");
   const int Kt = Ka + Kb;
-  fc1_reduce_kernel<<<(Kt + 1 + 255) / 256, 256, 0, st>>>(part, chunks, Kt, dw, db);
+  colsum_rows_kernel<<<(Kt + 1 + 31) / 32, 256, 0, st>>>(part, chunks, Kt + 1, Kt + 1, Kt, dw, db);   // rows are [dw(Kt) | db(1)]
   CTR_LAUNCHED("fc1_reduce");
   return CTR_OK;
 }

@@ -135,73 +135,100 @@ segsum_long_kernel(const float* __restrict__ g_rows, const float* __restrict__ g
   }
 }
 
-// Long runs split over SPLIT CTAs each (13 runs of B occurrences keep 13 CTAs busy otherwise): chunk c of run li sums
-// occurrences [c*len/SPLIT, (c+1)*len/SPLIT) with the same lane-group striding + fixed tree and writes a partial row;
-// segsum_long_final_kernel adds the SPLIT partials in chunk order.  Fixed shape => bit-reproducible.
-constexpr int SEG_SPLIT = 16;
+// Long runs split into chunks of SEG_CHUNK occurrences (the 13 continuous-feature ids of the Criteo layout occur B
+// times; DIN's padding id occurs ~10^6 times per step): segsum_long_plan_kernel gives every long run a range of partial
+// rows (base from an atomic counter -- which rows a run gets may differ from launch to launch, what is stored in them and
+// the order they are added in does not), segsum_long_split_kernel sums chunk c of run li with the lane-group striding +
+// fixed tree, segsum_long_final_kernel adds a run's partials in chunk order.  A run that does not get a range (scratch
+// exhausted) is summed by one CTA in the same kernel.  Fixed shapes => bit-reproducible.
+constexpr int SEG_CHUNK = 1024;
+
+// plan[0] = partial rows handed out; then per long run li: plan[1 + 2*li] = base row, plan[2 + 2*li] = number of chunks
+__global__ void segsum_long_plan_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restrict__ long_list,
+                                        int max_long, int cap_rows, int32_t* __restrict__ plan) {
+  const int n_long = min(long_list[0], max_long);
+  for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < n_long; li += gridDim.x * blockDim.x) {
+    const int u = long_list[1 + li];
+    const int len = seg_offsets[u + 1] - seg_offsets[u];
+    int chunks = (len + SEG_CHUNK - 1) / SEG_CHUNK;
+    int base = atomicAdd(&plan[0], chunks);
+    if (base + chunks > cap_rows) { base = -1; chunks = 1; }   // no room: whole run by one CTA, straight to the output
+    plan[1 + 2 * li] = base;
+    plan[2 + 2 * li] = chunks;
+  }
+}
 
 template <int LPR, int VEC>
 __global__ void __launch_bounds__(256)
 segsum_long_split_kernel(const float* __restrict__ g_rows, const float* __restrict__ g_w,
                          const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_offsets,
-                         const int32_t* __restrict__ long_list, int max_long, float* __restrict__ partial) {
+                         const int32_t* __restrict__ long_list, int max_long, const int32_t* __restrict__ plan,
+                         float* __restrict__ partial, float* __restrict__ g_uniq, float* __restrict__ gw_uniq) {
   constexpr int K = 4 * LPR * VEC;
   constexpr int G = 256 / LPR;
   __shared__ float4 sm[VEC][256];
   __shared__ float smw[G];
   const int g = threadIdx.x / LPR, c = threadIdx.x % LPR;
   const int n_long = min(long_list[0], max_long);
-  const int chunk = blockIdx.x;
   for (int li = blockIdx.y; li < n_long; li += gridDim.y) {
     const int u = long_list[1 + li];
     const int start0 = seg_offsets[u];
     const int len0 = seg_offsets[u + 1] - start0;
-    const int lo = (int)((int64_t)len0 * chunk / SEG_SPLIT), hi = (int)((int64_t)len0 * (chunk + 1) / SEG_SPLIT);
-    const int start = start0 + lo, len = hi - lo;
-    float4 acc[VEC];
+    const int base = plan[1 + 2 * li], chunks = plan[2 + 2 * li];
+    for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+      const int lo = base < 0 ? 0 : chunk * SEG_CHUNK, hi = base < 0 ? len0 : min(len0, lo + SEG_CHUNK);
+      const int start = start0 + lo, len = hi - lo;
+      float4 acc[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
-    float accw = 0.f;
-    for (int i = g; i < len; i += G) {
-      const int32_t p = perm[start + i];
-      const float4* row = reinterpret_cast<const float4*>(g_rows + (int64_t)p * K) + c;
+      for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
+      float accw = 0.f;
+      for (int i = g; i < len; i += G) {
+        const int32_t p = perm[start + i];
+        const float4* row = reinterpret_cast<const float4*>(g_rows + (int64_t)p * K) + c;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[v] = f4_add(acc[v], row[v * LPR]);
-      if (g_w && c == 0) accw += g_w[p];
-    }
+        for (int v = 0; v < VEC; ++v) acc[v] = f4_add(acc[v], row[v * LPR]);
+        if (g_w && c == 0) accw += g_w[p];
+      }
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) sm[v][threadIdx.x] = acc[v];
-    if (c == 0) smw[g] = accw;
-    __syncthreads();
-    for (int half = G / 2; half > 0; half >>= 1) {
-      if (g < half) {
+      for (int v = 0; v < VEC; ++v) sm[v][threadIdx.x] = acc[v];
+      if (c == 0) smw[g] = accw;
+      __syncthreads();
+      for (int half = G / 2; half > 0; half >>= 1) {
+        if (g < half) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v)
-          sm[v][threadIdx.x] = f4_add(sm[v][threadIdx.x], sm[v][threadIdx.x + half * LPR]);
-        if (c == 0) smw[g] += smw[g + half];
+          for (int v = 0; v < VEC; ++v)
+            sm[v][threadIdx.x] = f4_add(sm[v][threadIdx.x], sm[v][threadIdx.x + half * LPR]);
+          if (c == 0) smw[g] += smw[g + half];
+        }
+        __syncthreads();
+      }
+      if (g == 0) {
+        float* prow = base < 0 ? nullptr : partial + (int64_t)(base + chunk) * (K + 4);
+        float4* o = base < 0 ? reinterpret_cast<float4*>(g_uniq + (int64_t)u * K) + c : reinterpret_cast<float4*>(prow) + c;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) o[v * LPR] = sm[v][threadIdx.x];
+        if (c == 0) {
+          if (base < 0) { if (gw_uniq) gw_uniq[u] = smw[0]; }
+          else prow[K] = smw[0];
+        }
       }
       __syncthreads();
     }
-    if (g == 0) {
-      float* prow = partial + ((int64_t)li * SEG_SPLIT + chunk) * (K + 4);
-      float4* o = reinterpret_cast<float4*>(prow) + c;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) o[v * LPR] = sm[v][threadIdx.x];
-      if (c == 0) prow[K] = smw[0];
-    }
-    __syncthreads();
   }
 }
 
 __global__ void segsum_long_final_kernel(const float* __restrict__ partial, const int32_t* __restrict__ long_list,
-                                         int max_long, int K, float* __restrict__ g_uniq, float* __restrict__ gw_uniq) {
+                                         int max_long, const int32_t* __restrict__ plan, int K,
+                                         float* __restrict__ g_uniq, float* __restrict__ gw_uniq) {
   const int n_long = min(long_list[0], max_long);
   for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
+    const int base = plan[1 + 2 * li], chunks = plan[2 + 2 * li];
+    if (base < 0) continue;
     const int u = long_list[1 + li];
     for (int k = threadIdx.x; k <= K; k += blockDim.x) {
       if (k == K && !gw_uniq) continue;
       float s = 0.f;
-      for (int ch = 0; ch < SEG_SPLIT; ++ch) s += partial[((int64_t)li * SEG_SPLIT + ch) * (K + 4) + k];
+      for (int ch = 0; ch < chunks; ++ch) s += partial[(int64_t)(base + ch) * (K + 4) + k];
       if (k < K) g_uniq[(int64_t)u * K + k] = s;
       else gw_uniq[u] = s;
     }
@@ -247,11 +274,18 @@ extern "C" int ctr_segment_sum_rows(const float* g_rows, const float* g_w, const
               "ctr_segment_sum_rows: g_w and gw_uniq must both be given or both be NULL");
   cudaStream_t st = as_stream(stream);
   const int long_grid = 2 * sm_count();
-  // optional scratch (the K3 workspace is free by now): long runs split over SEG_SPLIT CTAs each
-  const int64_t max_long_possible = n / (CTR_LONG_SEG + 1) + 1;
-  const size_t split_need = (size_t)max_long_possible * SEG_SPLIT * (size_t)(K + 4) * sizeof(float);
-  const bool split = ws && ws_bytes >= split_need && ((uintptr_t)ws & 15) == 0;
-  float* partial = reinterpret_cast<float*>(ws);
+  // optional scratch (the K3 workspace is free by now): long runs are cut into chunks of SEG_CHUNK occurrences.
+  // layout: int32 plan[1 + 2*max_long] | float partial[cap_rows][K+4]
+  const int64_t max_long = n / (CTR_LONG_SEG + 1) + 1;
+  const size_t plan_bytes = ((size_t)(1 + 2 * max_long) * sizeof(int32_t) + 15) & ~(size_t)15;
+  const int64_t want_rows = n / SEG_CHUNK + max_long;       // every run: its full chunks + at most one partial chunk
+  int64_t cap_rows = 0;
+  if (ws && ws_bytes > plan_bytes && ((uintptr_t)ws & 15) == 0)
+    cap_rows = (int64_t)((ws_bytes - plan_bytes) / ((size_t)(K + 4) * sizeof(float)));
+  if (cap_rows > want_rows) cap_rows = want_rows;
+  const bool split = cap_rows >= 16;
+  int32_t* plan = reinterpret_cast<int32_t*>(ws);
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + plan_bytes);
 #define SEG_CASE(KK, LPR, VEC)                                                                      \
   case KK: {                                                                                        \
     unsigned blocks = (unsigned)ceil_div64(n * LPR, 256);                                           \
@@ -259,10 +293,13 @@ extern "C" int ctr_segment_sum_rows(const float* g_rows, const float* g_w, const
                                                           n, g_uniq, gw_uniq);                      \
     CTR_LAUNCHED("segsum_short");                                                                   \
     if (split) {                                                                                    \
-      segsum_long_split_kernel<LPR, VEC><<<dim3(SEG_SPLIT, 32), 256, 0, st>>>(                      \
-          g_rows, g_w, perm, seg_offsets, long_list, (int)max_long_possible, partial);              \
+      cudaMemsetAsync(plan, 0, sizeof(int32_t), st);                                                \
+      segsum_long_plan_kernel<<<8, 256, 0, st>>>(seg_offsets, long_list, (int)max_long, (int)cap_rows, plan); \
+      CTR_LAUNCHED("segsum_long_plan");                                                             \
+      segsum_long_split_kernel<LPR, VEC><<<dim3(64, 16), 256, 0, st>>>(                             \
+          g_rows, g_w, perm, seg_offsets, long_list, (int)max_long, plan, partial, g_uniq, gw_uniq); \
       CTR_LAUNCHED("segsum_long_split");                                                            \
-      segsum_long_final_kernel<<<64, 128, 0, st>>>(partial, long_list, (int)max_long_possible, K,   \
+      segsum_long_final_kernel<<<64, 128, 0, st>>>(partial, long_list, (int)max_long, plan, K,      \
                                                    g_uniq, gw_uniq);                                \
       CTR_LAUNCHED("segsum_long_final");                                                            \
     } else {                                                                                        \

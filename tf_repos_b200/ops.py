@@ -218,24 +218,37 @@ def dropout_mask(mask, keep_prob, seed, step_dev=None):
 BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default epsilon
 
 
+_bn_ws = {}
+
+
+def _bn_workspace(H: int, device) -> torch.Tensor:
+    key = (H, str(device))
+    if key not in _bn_ws:
+        _bn_ws[key] = torch.empty(max(int(_L.ctr_bn_workspace_bytes(H)), 16), dtype=torch.uint8, device=device)
+    return _bn_ws[key]
+
+
 def bn_fwd(x, gamma, beta, moving_mean, moving_var, train: bool, decay: float, drop_mask, keep_prob, out,
            save_mean=None, save_var=None):
     n, H = x.shape
+    ws = _bn_workspace(H, x.device)
     check(_L.ctr_bn_fwd(_p(x, torch.float32, "x"), n, H, _p(gamma, torch.float32, "gamma"),
                         _p(beta, torch.float32, "beta"), _p(moving_mean, torch.float32, "moving_mean"),
                         _p(moving_var, torch.float32, "moving_var"), int(train), float(decay), BN_EPS,
                         _p(drop_mask, torch.float32, "drop_mask"), float(keep_prob), _p(out, torch.float32, "out"),
-                        _p(save_mean, torch.float32, "save_mean"), _p(save_var, torch.float32, "save_var"), _stream()),
+                        _p(save_mean, torch.float32, "save_mean"), _p(save_var, torch.float32, "save_var"), _p(ws),
+                        ws.numel(), _stream()),
           "ctr_bn_fwd")
 
 
 def bn_bwd(d_out, x, save_mean, save_var, gamma, drop_mask, keep_prob, d_x, d_gamma, d_beta):
     n, H = x.shape
+    ws = _bn_workspace(H, x.device)
     check(_L.ctr_bn_bwd(_p(d_out, torch.float32, "d_out"), _p(x, torch.float32, "x"), n, H,
                         _p(save_mean, torch.float32, "save_mean"), _p(save_var, torch.float32, "save_var"),
                         _p(gamma, torch.float32, "gamma"), BN_EPS, _p(drop_mask, torch.float32, "drop_mask"),
                         float(keep_prob), _p(d_x, torch.float32, "d_x"), _p(d_gamma, torch.float32, "d_gamma"),
-                        _p(d_beta, torch.float32, "d_beta"), _stream()), "ctr_bn_bwd")
+                        _p(d_beta, torch.float32, "d_beta"), _p(ws), ws.numel(), _stream()), "ctr_bn_bwd")
 
 
 def cross_fwd(x0, w, b, xL, s):
