@@ -81,3 +81,18 @@ def test_route_plan_properties():
         assert np.all(np.diff(own) >= 0)                               # bucket-major
         assert np.array_equal(local_ids * G + own, uniq[order])        # id = local*G + owner
         assert sum(dp.local_rows(10_000, G, r) for r in range(G)) == 10_000
+
+
+def test_composite_key_plan_equals_route_plan():
+    """one sort of owner*ceil(N/G)+local keys == unique by id + stable bucket by owner (the two ways of routing)"""
+    import numpy as np
+    from tf_repos_b200 import dist_plan as dp
+    rng = np.random.default_rng(0)
+    for N, G in ((50_000, 1), (50_001, 2), (49_999, 3), (1_000_003, 8)):
+        ids = rng.integers(0, N, size=30_000)
+        uniq = np.unique(ids)
+        counts, order, local = dp.route_plan(uniq, G)
+        c2, l2, pos = dp.key_plan(ids, N, G)
+        assert np.array_equal(counts, c2) and np.array_equal(local, l2)
+        cache_ids = l2 * G + np.repeat(np.arange(G), c2)
+        assert np.array_equal(cache_ids[pos], ids)

@@ -29,3 +29,19 @@ def route_plan(uniq: np.ndarray, G: int) -> Tuple[np.ndarray, np.ndarray, np.nda
 
 def split_sizes(counts: np.ndarray) -> List[int]:
     return [int(c) for c in counts]
+
+
+def composite_keys(ids: np.ndarray, N: int, G: int) -> np.ndarray:
+    """key(id) = owner * ceil(N/G) + local row: sorting the keys orders ids by (owner, id) -- what csrc/shard.cu's
+    ctr_shard_keys emits and tf_repos_b200/sharded.py sorts (one radix sort per step)."""
+    npad = (N + G - 1) // G
+    return owner_of(ids, G) * npad + local_row(ids, G)
+
+
+def key_plan(ids: np.ndarray, N: int, G: int):
+    """(counts [G], local_ids [U] bucket-major, cache_pos [n]) from the composite keys of a batch's ids."""
+    npad = (N + G - 1) // G
+    keys = composite_keys(ids.astype(np.int64), N, G)
+    uniq, inverse = np.unique(keys, return_inverse=True)
+    own = uniq // npad
+    return np.bincount(own, minlength=G).astype(np.int64), (uniq - own * npad).astype(np.int64), inverse.astype(np.int64)

@@ -131,12 +131,17 @@ def run(build_model: Callable[[], object], model_name: str):
 
     if FLAGS.task_type == "train":
         t0, s0 = time.time(), model.global_step
+        t_ckpt = time.time()          # RunConfig default save_checkpoints_secs = 600 (the reference does not override it)
         last = None
         for ids, vals, labels in batches(tr_files, FLAGS.num_epochs):
             step_fn = getattr(model, "train_step_graphed", model.train_step)   # full batches replay a CUDA graph
             last = step_fn(ids, vals, labels)
             if model.global_step % FLAGS.log_steps == 0:
                 model.check_ids()       # TF fails on the first bad batch; here: at the next log point, before more damage
+                if time.time() - t_ckpt >= 600.0:
+                    save_checkpoint(model, FLAGS.model_dir)
+                    print("INFO:Saving checkpoints for %d into %s." % (model.global_step, FLAGS.model_dir))
+                    t_ckpt = time.time()
                 dt = time.time() - t0
                 print("INFO:global_step/sec: %g  samples/sec: %g" % ((model.global_step - s0) / dt,
                                                                       (model.global_step - s0) * FLAGS.batch_size / dt))
