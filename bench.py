@@ -268,6 +268,8 @@ def main_b200(args):
         torch.cuda.synchronize()
 
     use_graphs = world == 1 and os.environ.get("CTR_BENCH_GRAPHS", "1") != "0"
+    if sharded:      # the compute segment between the two exchanges replays from one CUDA graph (sharded.py)
+        model.use_graphs = os.environ.get("CTR_BENCH_GRAPHS", "1") != "0"
 
     def train(ids, vals, labels):
         # public API either way; the graphed form replays the step's launches from a CUDA graph (same kernels, same

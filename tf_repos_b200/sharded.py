@@ -152,6 +152,45 @@ class ShardedDeepFM:
         self._a = self.mlp.forward_hidden(self.x[:B], self.dense, train, masks, step_dev=self.opt.state[3:4])
         return self.mlp.forward_out(self._a, self.dense)
 
+    # ---- everything between the row exchange and the gradient exchange: K1 on the row cache, MLP forward, loss head,
+    # MLP backward, K2, per-cache-row gradient sums.  Static shapes and addresses (the cache is indexed through
+    # uw.inverse, sizes live on the device) => replayed from ONE CUDA graph; the exchanges around it need host-side
+    # split sizes and stay eager.
+    def _compute_eager(self, vals, labels, masks=None):
+        B, F, K, G = self.B, self.F, self.K, self.G
+        rid = self.uw.inverse[: B * F].view(B, F)
+        ops.fm_embed_fwd(rid, vals, self.cache_v, self.cache_w, ops.FM_DEEPFM, x=self.x, y_w=self.y_w, y2=self.y_v,
+                         S=self.S, oob=self.oob)
+        self._a = self.mlp.forward_hidden(self.x, self.dense, True, masks, step_dev=self.opt.state[3:4])
+        y_d = self.mlp.forward_out(self._a, self.dense)
+        ops.logit_loss(self.dense["fm_bias"], self.y_w, self.y_v, y_d, labels, B, y=self.y, pred=self.pred,
+                       loss_ce=self.loss_ce, dy=self.dy, dbias=self.dense.grads["fm_bias"], B_total=B * G)
+        self.mlp.backward_out(self._a, self.dy, self.dense, self.d_last)
+        dX = self.mlp.backward_hidden(self.x, self.d_last, self.dense)
+        ops.fm_embed_bwd(vals, self.x, self.S, dX, self.dy, self.dy, K, ops.FM_DEEPFM, self.g_rows, self.g_w)
+        # per cache row: the lookup's sort already grouped the occurrences in cache order
+        ops.segment_sum_rows(self.g_rows, self.g_w, self.uw, K, self.g_cache, self.gw_cache)
+
+    def _compute(self, vals, labels, masks=None):
+        if masks is not None or not self.use_graphs:
+            return self._compute_eager(vals, labels, masks)
+        if not hasattr(self, "_cg"):
+            self._cg, self._cg_seen = None, 0
+            self._cvals = torch.empty(self.B, self.F, dtype=torch.float32, device=self.device)
+            self._clabels = torch.empty(self.B, dtype=torch.float32, device=self.device)
+        self._cvals.copy_(vals, non_blocking=True); self._clabels.copy_(labels, non_blocking=True)
+        if self._cg is None:
+            self._cg_seen += 1
+            if self._cg_seen < 3:        # warm-up visits run eagerly (lazy allocations, cudaFuncSetAttribute)
+                return self._compute_eager(self._cvals, self._clabels)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):   # NCCL's watchdog thread keeps polling
+                self._compute_eager(self._cvals, self._clabels)
+            self._cg = g
+        self._cg.replay()
+
+    use_graphs = True
+
     def predict(self, ids, vals):
         B = ids.shape[0]
         assert B == self.B
@@ -175,14 +214,7 @@ class ShardedDeepFM:
         else:
             self.opt.tick()
         U, send, recv, R = self._lookup(ids, deferred_j=(self.epoch_pos if deferred else None))
-        y_d = self._forward(ids, vals, U, train=True, masks=masks)
-        ops.logit_loss(self.dense["fm_bias"], self.y_w, self.y_v, y_d, labels, B, y=self.y, pred=self.pred,
-                       loss_ce=self.loss_ce, dy=self.dy, dbias=self.dense.grads["fm_bias"], B_total=B * G)
-        self.mlp.backward_out(self._a, self.dy, self.dense, self.d_last)
-        dX = self.mlp.backward_hidden(self.x, self.d_last, self.dense)
-        ops.fm_embed_bwd(vals, self.x, self.S, dX, self.dy, self.dy, K, ops.FM_DEEPFM, self.g_rows, self.g_w)
-        # per cache row: the lookup's sort already grouped the occurrences in cache order
-        ops.segment_sum_rows(self.g_rows, self.g_w, self.uw, K, self.g_cache, self.gw_cache)
+        self._compute(vals, labels, masks)
         self._a2a(self.recv_g[:R], self.g_cache[:U], recv, send)
         self._a2a(self.recv_gw[:R], self.gw_cache[:U], recv, send)
         if G > 1:
