@@ -359,6 +359,40 @@ __device__ __forceinline__ void ws_load_tile(float4 (&r)[4], const float* __rest
   }
 }
 
+// Interior tiles and full 32-wide slices (all of a layer but its edges): no bounds logic, pointers advanced by the
+// caller.  `base` already points at this thread's first element of slice 0 (RC: row (wrow+sub), 16 B chunk ch;
+// !RC: tile row tid&127, reduction index (tid>>7)*16); r0 is the slice's offset along the reduction.
+template <bool RC>
+__device__ __forceinline__ void ws_load_tile_fast(float4 (&r)[4], const float* __restrict__ base, int ld, int r0) {
+  if (RC) {
+    const float* p = base + r0;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) r[it] = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(it * 4) * ld));
+  } else {
+    const float* p = base + (int64_t)r0 * ld;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      r[c].x = __ldg(p + (int64_t)(4 * c) * ld);
+      r[c].y = __ldg(p + (int64_t)(4 * c + 1) * ld);
+      r[c].z = __ldg(p + (int64_t)(4 * c + 2) * ld);
+      r[c].w = __ldg(p + (int64_t)(4 * c + 3) * ld);
+    }
+  }
+}
+
+// hi/lo split + store with the swizzled offsets precomputed once per thread (they do not depend on the slice)
+__device__ __forceinline__ void ws_store_tile_fast(const float4 (&r)[4], uint8_t* hi_tile, uint8_t* lo_tile,
+                                                   const uint32_t (&off)[4]) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    float4 hi, lo;
+    hi.x = tf32_hi(r[it].x); hi.y = tf32_hi(r[it].y); hi.z = tf32_hi(r[it].z); hi.w = tf32_hi(r[it].w);
+    lo.x = r[it].x - hi.x; lo.y = r[it].y - hi.y; lo.z = r[it].z - hi.z; lo.w = r[it].w - hi.w;
+    *reinterpret_cast<float4*>(hi_tile + off[it]) = hi;
+    *reinterpret_cast<float4*>(lo_tile + off[it]) = lo;
+  }
+}
+
 template <bool RC>
 __device__ __forceinline__ void ws_store_tile(const float4 (&r)[4], uint8_t* hi_tile, uint8_t* lo_tile, int tid) {
   const int sub = (tid & 31) >> 3, ch = tid & 7, wrow = (tid >> 5) * 16;
@@ -449,9 +483,28 @@ tc_gemm_ws_kernel(const float* __restrict__ A, int lda, const float* __restrict_
 
   // ---------------- producers ----------------
   {
+    // per-thread constants of the fast path
+    const int sub = (tid & 31) >> 3, ch = tid & 7, wrow = (tid >> 5) * 16;
+    uint32_t offA[4], offB[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      offA[it] = A_RC ? sw128_off(wrow + it * 4 + sub, ch) : sw128_off(tid & 127, (tid >> 7) * 4 + it);
+      offB[it] = B_RC ? sw128_off(wrow + it * 4 + sub, ch) : sw128_off(tid & 127, (tid >> 7) * 4 + it);
+    }
+    const float* baseA = A_RC ? A + (int64_t)(i0 + wrow + sub) * lda + ch * 4 : A + (int64_t)((tid >> 7) * 16) * lda + i0 + (tid & 127);
+    const float* baseB = B_RC ? B + (int64_t)(j0 + wrow + sub) * ldb + ch * 4 : B + (int64_t)((tid >> 7) * 16) * ldb + j0 + (tid & 127);
+    // interior tile, and 16 B alignment of every float4 the RC path reads
+    const bool fullA = (i0 + TC_BM <= M) && (!A_RC || (((lda & 3) == 0) && ((((uintptr_t)A) & 15) == 0) && ((r_begin & 3) == 0)));
+    const bool fullB = (j0 + TC_BM <= N) && (!B_RC || (((ldb & 3) == 0) && ((((uintptr_t)B) & 15) == 0) && ((r_begin & 3) == 0)));
+    auto load_slice = [&](float4 (&a)[4], float4 (&b)[4], int kt) {
+      const int r0 = r_begin + kt * TC_BK;
+      const bool whole = r0 + TC_BK <= r_end;
+      if (fullA && whole) ws_load_tile_fast<A_RC>(a, baseA, lda, r0); else ws_load_tile<A_RC>(a, A, lda, i0, M, r0, r_end, tid);
+      if (fullB && whole) ws_load_tile_fast<B_RC>(b, baseB, ldb, r0); else ws_load_tile<B_RC>(b, B, ldb, j0, N, r0, r_end, tid);
+    };
     float4 ra[2][4], rb[2][4];
-    if (KT > 0) { ws_load_tile<A_RC>(ra[0], A, lda, i0, M, r_begin, r_end, tid); ws_load_tile<B_RC>(rb[0], B, ldb, j0, N, r_begin, r_end, tid); }
-    if (KT > 1) { ws_load_tile<A_RC>(ra[1], A, lda, i0, M, r_begin + TC_BK, r_end, tid); ws_load_tile<B_RC>(rb[1], B, ldb, j0, N, r_begin + TC_BK, r_end, tid); }
+    if (KT > 0) load_slice(ra[0], rb[0], 0);
+    if (KT > 1) load_slice(ra[1], rb[1], 1);
     for (int kt0 = 0; kt0 < KT; kt0 += 2) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -460,15 +513,11 @@ tc_gemm_ws_kernel(const float* __restrict__ A, int lda, const float* __restrict_
           const int s = kt % WS_STAGES;
           if (kt >= WS_STAGES) mbar_wait_ws(&bar_empty[s], (uint32_t)(((kt / WS_STAGES) - 1) & 1));
           uint8_t* st = smem + s * TC_STAGE_BYTES;
-          ws_store_tile<A_RC>(ra[u], st, st + TC_TILE_BYTES, tid);
-          ws_store_tile<B_RC>(rb[u], st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, tid);
+          ws_store_tile_fast(ra[u], st, st + TC_TILE_BYTES, offA);
+          ws_store_tile_fast(rb[u], st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, offB);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_arrive(&bar_full[s]);
-          if (kt + 2 < KT) {
-            const int r0 = r_begin + (kt + 2) * TC_BK;
-            ws_load_tile<A_RC>(ra[u], A, lda, i0, M, r0, r_end, tid);
-            ws_load_tile<B_RC>(rb[u], B, ldb, j0, N, r0, r_end, tid);
-          }
+          if (kt + 2 < KT) load_slice(ra[u], rb[u], kt + 2);
         }
       }
     }
