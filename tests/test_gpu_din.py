@@ -107,3 +107,46 @@ def test_din_single_position_known_answer():
     ops.din_pool_fwd(E, z, ids, B, 1, K, att, u, K)
     ref = E * torch.sigmoid(z)[:, None] * (ids > 0).float()[:, None]
     assert torch.allclose(u, ref, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("mode", ["exact", "exact_deferred"])
+def test_din_partial_final_batch_equals_the_smaller_batch(mode):
+    """repeat-before-batch leaves one partial batch at the end of training (DIN.py:93-94): the CUDA model takes it padded
+    to its buffer size with n_valid; the step must equal the oracle's step on the n_valid-sample batch."""
+    from oracle import models as om
+    from tf_repos_b200 import synth
+    from tf_repos_b200.din import DIN
+    B, n, N, K, Fp, P = 64, 23, 5000, 8, 11, 9
+    kw = dict(deep_layers="16,8", dropout="1.0,1.0", attention_layers="256", attention_pooling=True, l2_reg=1e-4,
+              learning_rate=5e-4, optimizer="Adam")
+    ref = om.DIN(Fp, N, K, update_mode="exact", seed=4, **kw)
+    g = torch.Generator().manual_seed(1)
+    ref.params["embeddings"].copy_(torch.randn(N, K, generator=g) * 0.1)
+    gpu = DIN(Fp, N, K, B, P, max_a_int=8, update_mode=mode, epoch_steps=3, device="cuda:0", **kw)
+    gpu.load_variables(ref.params)
+    # one full step, then the partial one
+    batch, labels = synth.din_batch(B, N, Fp, P, 8, seed=7)
+    ref.train_step({k: (v.long() if v.dtype == torch.int32 else v) for k, v in batch.items()}, labels)
+    gpu.train_step(_cuda(batch), labels.cuda())
+    small, lab_s = synth.din_batch(n, N, Fp, P, 8, seed=8)
+    loss_ref = ref.train_step({k: (v.long() if v.dtype == torch.int32 else v) for k, v in small.items()}, lab_s)
+    # pad to B with copies of sample 0 (what din_main.make_batch does)
+    pad = B - n
+    off = small["a_int_off"]
+    first_bag = small["a_int_ids"][off[0]:off[1]]
+    padded = {
+        "feat_ids": torch.cat([small["feat_ids"], small["feat_ids"][:1].repeat(pad, 1)]),
+        "a_ids": torch.cat([small["a_ids"], small["a_ids"][:, :1].repeat(1, pad)], dim=1),
+        "a_int_ids": torch.cat([small["a_int_ids"], first_bag.repeat(pad)]),
+        "a_int_off": torch.cat([off, off[-1] + (torch.arange(1, pad + 1, dtype=off.dtype) * first_bag.numel())]),
+        "u_ids": torch.cat([small["u_ids"], small["u_ids"][:, :1].repeat(1, pad, 1)], dim=1),
+        "u_wgt": torch.cat([small["u_wgt"], small["u_wgt"][:, :1].repeat(1, pad, 1)], dim=1),
+    }
+    labels_p = torch.cat([lab_s, lab_s[:1].repeat(pad)])
+    parts = gpu.train_step(_cuda(padded), labels_p.cuda(), n_valid=n)
+    if mode == "exact":
+        assert abs(gpu.loss_value(parts) - loss_ref) <= 1e-5 * abs(loss_ref), (gpu.loss_value(parts), loss_ref)
+    vs = gpu.variables()
+    for name in ("embeddings", "MLP-layer/mlp0/weights", "DIN-out/din_out/weights", "Field-wise-Pooling-layer/att_fc0/weights",
+                 "Field-wise-Pooling-layer/att_out/biases"):
+        _close(vs[name], ref.params[name], 2e-5, f"{name} after the partial batch ({mode})")

@@ -259,8 +259,14 @@ class DIN:
         g[o: o + n].zero_()
         ops.bag_sum_bwd(self.d_aint, K, None, batch["a_int_off"], K, g[o:])
 
-    def train_step(self, batch, labels, masks=None) -> torch.Tensor:
-        """one optimizer.minimize(loss) (DIN.py:226-247).  Returns {mean CE, l2*l2_loss(embeddings)}."""
+    def train_step(self, batch, labels, masks=None, n_valid: Optional[int] = None) -> torch.Tensor:
+        """one optimizer.minimize(loss) (DIN.py:226-247).  Returns {mean CE, l2*l2_loss(embeddings)}.
+        n_valid < batch_size: the final partial batch `repeat`-before-`batch` leaves (DIN.py:93-94), padded to the
+        configured batch size by the caller.  The loss is the mean over the n_valid real samples and the padded rows'
+        dy is exactly 0, so their gradient rows, dZ rows and bias terms are exact zeros: the step equals TensorFlow's
+        step on the n_valid-sample batch (a padded id that enters the de-duplicated update with a zero summed gradient
+        takes g = 0 + l2*var, which is the untouched-row update it would have taken anyway).  Not with --batch_norm
+        (the padded rows would enter the batch moments)."""
         upd = self.updater
         deferred = self.update_mode == "exact_deferred"
         self._stage_ids(batch)
@@ -274,7 +280,14 @@ class DIN:
         else:
             self.opt.tick()
         y_d = self._forward(batch, train=True, masks=masks)
-        ops.logit_loss(None, y_d, None, None, labels, self.B, y=self.y, pred=self.pred, loss_ce=self.loss_ce, dy=self.dy)
+        n = self.B if n_valid is None else int(n_valid)
+        assert 0 < n <= self.B
+        if n < self.B:
+            if self.mlp.batch_norm:
+                raise NotImplementedError("a partial final batch with --batch_norm (padded rows would enter the batch moments)")
+            self.dy[n:].zero_()
+        ops.logit_loss(None, y_d[:n], None, None, labels[:n], n, y=self.y[:n], pred=self.pred[:n], loss_ce=self.loss_ce,
+                       dy=self.dy[:n])
         self._backward(batch)
         if deferred:
             upd.segment_sum(self.g_all, None)

@@ -8,9 +8,9 @@ Q6, DIN.py:342-345) with the features of DIN.py:60-77:
 (sparse_tensor_to_dense, DIN.py:153-154): here every batch is padded to the longest list of the whole input (P),
 which gives the same numbers because id 0 is masked out (DIN.py:157).
 
-Deviation (documented): the CUDA DIN model works on full batches; the single partial batch that
-repeat-before-batch leaves at the very end of TRAINING is skipped with a log line (TensorFlow would take one more,
-smaller step).  eval / infer pad the last batch and drop the padded outputs, so every sample is scored.
+The CUDA DIN model works on full-size buffers; the single partial batch that repeat-before-batch leaves at the very end
+of TRAINING is padded and trained on with `n_valid` (the padded rows' dy is exactly 0: same step as TensorFlow's smaller
+batch, see DIN.train_step); eval / infer pad the last batch and drop the padded outputs, so every sample is scored.
 """
 from __future__ import annotations
 
@@ -165,11 +165,8 @@ def run():
     if FLAGS.task_type == "train":
         t0, s0, last = time.time(), model.global_step, None
         for idx in index_stream(len(tr["y"]), FLAGS.num_epochs, B):
-            if len(idx) < B:
-                print("INFO:skipping the final partial batch of %d samples (full batches only on the CUDA DIN path)" % len(idx))
-                break
-            batch, labels, _ = make_batch(tr, idx, B, P, dev)
-            last = model.train_step(batch, labels)
+            batch, labels, n = make_batch(tr, idx, B, P, dev)
+            last = model.train_step(batch, labels, n_valid=n)      # the final batch may be partial (kept, DIN.py:93-94)
             if model.global_step % FLAGS.log_steps == 0:
                 dt = time.time() - t0
                 print("INFO:global_step/sec: %g" % ((model.global_step - s0) / dt))
