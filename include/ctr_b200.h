@@ -302,6 +302,14 @@ int ctr_din_pool_fwd(const float* E, const float* z, const int32_t* ids, int B, 
 int ctr_din_pool_bwd(const float* E, const float* att, const int32_t* ids, const float* du, int64_t ld_u, int B,
                      int P, int K, float* dE, float* dz, ctr_stream_t stream);
 int ctr_group_sum(const float* dZ, int B, int P, int N, float* dU, ctr_stream_t stream);
+/* Attention unit backward through the N=1 output and the hidden layer's relu/dropout in ONE pass over the [B*P, H] hidden
+ * activations Hh (autodiff of DIN.py:164-169): dZ[r][c] = dz[r]*w2[c] (*mask/keep) where Hh > 0; dU[b][c] = sum_p dZ
+ * (the group-bias gradient; colsum(dU) is the layer's bias gradient); gw2_part[b][c] = sum_p dz*Hh (colsum = the output
+ * layer's weight gradient).  Then ctr_fc_bwd(act = 2) takes dZ as is. */
+int ctr_din_att_dz(const float* Hh, const float* drop_mask, float keep_prob, const float* dz, const float* w2, int B, int P,
+                   int H, float* dZ, float* dU, float* gw2_part, ctr_stream_t stream);
+/* out[k] = sum_r part[r*ld + k], k < ncols: deterministic column sums of many rows (fixed order) */
+int ctr_colsum_rows(const float* part, int rows, int ld, int ncols, float* out, ctr_stream_t stream);
 int ctr_axpby(const float* a, float alpha, const float* b, float beta, int64_t n, float* out, ctr_stream_t stream);
 
 /* ---- K7/K8: all-pairs interactions (pair order i < j row-major; P = F(F-1)/2) -----------------------

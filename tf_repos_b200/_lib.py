@@ -80,6 +80,8 @@ SIGNATURES = {
     "ctr_din_pool_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int64, P]),
     "ctr_din_pool_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P]),
     "ctr_group_sum": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "ctr_din_att_dz": (c_int, [P, P, c_float, P, P, c_int, c_int, c_int, P, P, P, P]),
+    "ctr_colsum_rows": (c_int, [P, c_int, c_int, c_int, P, P]),
     "ctr_axpby": (c_int, [P, c_float, P, c_float, c_int64, P, P]),
     "ctr_pnn_product_fwd": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "ctr_pnn_product_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),

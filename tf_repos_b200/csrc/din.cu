@@ -214,6 +214,38 @@ using namespace ctr;
       return CTR_ERR_UNSUPPORTED;                                                                  \
   }
 
+
+// ---- attention unit backward, the [B*P, H] hidden layer in ONE pass ------------------------------------------
+// Replaces three passes over the hidden activations of a behaviour field (autodiff of DIN.py:164-169):
+//   fc1_bwd   dHh[r][c] = dz[r]*w2[c]                      (+ gw2 = sum_r dz[r]*Hh[r][c], gb2 = sum_r dz[r])
+//   fc_dz     dZ = dHh*mask/keep * (Hh > 0)                (+ db1 = colsum dZ)
+//   group_sum dU[b][c] = sum_p dZ[b*P+p][c]
+// One CTA per sample (its P rows are contiguous); a thread owns column(s) c, walks the P rows, writes dZ, and keeps
+// sum_p dZ (= dU row b; db1 = colsum(dU)) and sum_p dz*Hh (gw2 partial row b) in registers: no atomics, fixed order.
+__global__ void __launch_bounds__(256)
+din_att_dz_kernel(const float* __restrict__ Hh, const float* __restrict__ mask, float keep, const float* __restrict__ dz,
+                  const float* __restrict__ w2, int P, int H, float* __restrict__ dZ, float* __restrict__ dU,
+                  float* __restrict__ gw2_part) {
+  const int b = blockIdx.x;
+  const int64_t row0 = (int64_t)b * P;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    const float wc = w2[c];
+    float su = 0.f, sg = 0.f;
+    for (int p = 0; p < P; ++p) {
+      const int64_t i = (row0 + p) * H + c;
+      const float d0 = dz[row0 + p], h = Hh[i];
+      float d = d0 * wc;
+      if (mask) d = __fdiv_rn(d * mask[i], keep);
+      if (!(h > 0.f)) d = 0.f;
+      dZ[i] = d;
+      su += d;
+      sg = fmaf(h, d0, sg);
+    }
+    dU[(int64_t)b * H + c] = su;
+    gw2_part[(int64_t)b * H + c] = sg;
+  }
+}
+
 extern "C" {
 
 int ctr_gather_scale_rows(const int32_t* ids, const float* wgt, const float* V, int64_t N, int64_t n, int K,
@@ -306,6 +338,17 @@ int ctr_group_sum(const float* dZ, int B, int P, int N, float* dU, ctr_stream_t 
   CTR_REQUIRE(dZ && dU, CTR_ERR_INVALID_ARG, "ctr_group_sum: null buffer");
   group_sum_kernel<<<B, 256, 0, as_stream(stream)>>>(dZ, B, P, N, dU);
   CTR_LAUNCHED("ctr_group_sum");
+  return CTR_OK;
+}
+
+int ctr_din_att_dz(const float* Hh, const float* drop_mask, float keep_prob, const float* dz, const float* w2, int B, int P,
+                   int H, float* dZ, float* dU, float* gw2_part, ctr_stream_t stream) {
+  CTR_REQUIRE(B >= 0 && P > 0 && H > 0, CTR_ERR_INVALID_ARG, "ctr_din_att_dz: bad shape");
+  if (B == 0) return CTR_OK;
+  CTR_REQUIRE(Hh && dz && w2 && dZ && dU && gw2_part, CTR_ERR_INVALID_ARG, "ctr_din_att_dz: null buffer");
+  CTR_REQUIRE(!drop_mask || keep_prob > 0.f, CTR_ERR_INVALID_ARG, "ctr_din_att_dz: keep_prob must be > 0 with a mask");
+  din_att_dz_kernel<<<B, 256, 0, as_stream(stream)>>>(Hh, drop_mask, keep_prob, dz, w2, P, H, dZ, dU, gw2_part);
+  CTR_LAUNCHED("ctr_din_att_dz");
   return CTR_OK;
 }
 

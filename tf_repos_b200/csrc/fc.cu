@@ -324,9 +324,10 @@ size_t ctr_fc_bwd_workspace_bytes(int M, int Kd, int Nd) {
 int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* drop_mask, float keep_prob,
                float* dOut, int M, int Kd, int Nd, int act, float* dIn, int accumulate_din, float* dW, float* db,
                void* ws, size_t ws_bytes, ctr_stream_t stream) {
-  CTR_REQUIRE(M >= 0 && Kd > 0 && Nd > 0 && (act == 0 || act == 1), CTR_ERR_INVALID_ARG, "ctr_fc_bwd: bad shape/act");
+  // act == 2: dOut already holds dZ and the caller has the bias gradient (ctr_din_att_dz): skip the dZ pass
+  CTR_REQUIRE(M >= 0 && Kd > 0 && Nd > 0 && (act == 0 || act == 1 || act == 2), CTR_ERR_INVALID_ARG, "ctr_fc_bwd: bad shape/act");
   if (M == 0) return CTR_OK;
-  CTR_REQUIRE(in && Wt && out && dOut && dW && db, CTR_ERR_INVALID_ARG, "ctr_fc_bwd: null buffer");
+  CTR_REQUIRE(in && Wt && dOut && dW && (act == 2 || (out && db)), CTR_ERR_INVALID_ARG, "ctr_fc_bwd: null buffer");
   CTR_REQUIRE(ws && ws_bytes >= ctr_fc_bwd_workspace_bytes(M, Kd, Nd), CTR_ERR_WORKSPACE,
               "ctr_fc_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
@@ -334,10 +335,12 @@ int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* 
   const int chunks = (M + DZ_ROWS - 1) / DZ_ROWS;
   float* dw_part = colsum + (size_t)chunks * Nd;
   // 1. dZ in place + bias gradient
-  fc_dz_kernel<<<dim3((Nd + 31) / 32, chunks), 256, 0, st>>>(dOut, out, drop_mask, keep_prob, M, Nd, act, colsum);
-  CTR_LAUNCHED("fc_dz");
-  colsum_rows_kernel<<<(Nd + 31) / 32, 256, 0, st>>>(colsum, chunks, Nd, Nd, Nd, db, nullptr);
-  CTR_LAUNCHED("fc_db_reduce");
+  if (act != 2) {
+    fc_dz_kernel<<<dim3((Nd + 31) / 32, chunks), 256, 0, st>>>(dOut, out, drop_mask, keep_prob, M, Nd, act, colsum);
+    CTR_LAUNCHED("fc_dz");
+    colsum_rows_kernel<<<(Nd + 31) / 32, 256, 0, st>>>(colsum, chunks, Nd, Nd, Nd, db, nullptr);
+    CTR_LAUNCHED("fc_db_reduce");
+  }
   // 2. dW[Kd,Nd] = in^T @ dZ, split over M
   // narrow layer input (DIN attention: Kd = 32, Nd = 256, M = B*P = 409600): as in^T @ dZ the 128-row MMA tile
   // would be 3/4 padding; the transposed product dW^T[Nd,Kd] = dZ^T @ in fills it (and its N = Kd MMAs are 4x smaller)
@@ -378,6 +381,14 @@ int ctr_fc_bwd(const float* in, const float* Wt, const float* out, const float* 
                                                                            0, nullptr, 1.f, nullptr, 1);
     CTR_LAUNCHED("fc_din");
   }
+  return CTR_OK;
+}
+
+int ctr_colsum_rows(const float* part, int rows, int ld, int ncols, float* out, ctr_stream_t stream) {
+  CTR_REQUIRE(rows >= 0 && ncols > 0 && ld >= ncols, CTR_ERR_INVALID_ARG, "ctr_colsum_rows: bad shape");
+  CTR_REQUIRE(part && out, CTR_ERR_INVALID_ARG, "ctr_colsum_rows: null buffer");
+  colsum_rows_kernel<<<(ncols + 31) / 32, 256, 0, as_stream(stream)>>>(part, rows, ld, ncols, ncols, out, nullptr);
+  CTR_LAUNCHED("ctr_colsum_rows");
   return CTR_OK;
 }
 

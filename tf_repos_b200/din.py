@@ -106,6 +106,8 @@ class DIN:
             self.dz = torch.empty(B * P, **f32)
             self.dHh = torch.empty(B * P, H, **f32)
             self.dU = torch.empty(B, H, **f32)
+            self.gw2_part = torch.empty(B, H, **f32)
+            self.dz_b = torch.empty(P, **f32)
             self.da = [torch.empty(B, K, **f32) for _ in range(4)]
             self.gWc = torch.zeros(4, K, H, **f32)
             self.gWd = torch.zeros(4, K, H, **f32)
@@ -224,10 +226,15 @@ class DIN:
             for f in range(4):
                 ids_f = batch["u_ids"][f].reshape(-1)
                 ops.din_pool_bwd(self.E[f], self.att[f], ids_f, dx[:, self.off_u + f * K:], Dx, B, P, K, self.dE, self.dz)
-                ops.fc1_bwd(self.Hh[f], None, w2, self.dz, self.dHh, None, self.gw2[f], self.gb2[f], self.att_ws)
-                ops.fc_bwd(self.E[f], self.Wc, self.Hh[f], self._att_active[f], self.keep[0], self.dHh, 1, self.dE,
-                           self.gWc[f], self.gb1[f], self.att_ws, accumulate_din=True)
-                ops.group_sum(self.dHh, B, P, H, self.dU)                      # dHh now holds dZ
+                # output layer + relu/dropout backward + per-sample sums in ONE pass over Hh (csrc/din.cu din_att_dz_kernel)
+                ops.din_att_dz(self.Hh[f], self._att_active[f], self.keep[0], self.dz, w2, B, P, self.dHh, self.dU,
+                               self.gw2_part)
+                ops.colsum_rows(self.gw2_part, self.gw2[f])                   # d att_out/weights
+                ops.colsum_rows(self.dz.view(B, P), self.dz_b)                # d att_out/biases = sum(dz): per-position sums ...
+                ops.colsum_rows(self.dz_b.view(P, 1), self.gb2[f])            # ... then over positions (fixed order)
+                ops.colsum_rows(self.dU, self.gb1[f])                         # d att_fc0/biases = colsum(dZ) = colsum(dU)
+                ops.fc_bwd(self.E[f], self.Wc, None, None, 1.0, self.dHh, 2, self.dE, self.gWc[f], None, self.att_ws,
+                           accumulate_din=True)                               # dHh holds dZ: dWc, dE += dZ @ Wc^T
                 ops.fc_bwd(self.a_c[f], self.Wd, self.U, None, 1.0, self.dU, 0, self.da[f], self.gWd[f], self.scratch_b,
                            self.att_ws)
                 ops.scale_rows(self.dE, None, batch["u_wgt"][f].reshape(-1), B * P, K, 1, K, g[s[f"u{f}"][0]:])

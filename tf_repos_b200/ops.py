@@ -320,6 +320,20 @@ def din_pool_bwd(E, att, ids, du_view, ld_u, B, P, K, dE, dz):
                               _stream()), "ctr_din_pool_bwd")
 
 
+def din_att_dz(Hh, mask, keep, dz, w2, B, P, dZ, dU, gw2_part):
+    H = Hh.shape[1]
+    check(_L.ctr_din_att_dz(_p(Hh, torch.float32, "Hh"), _p(mask, torch.float32, "mask"), float(keep),
+                            _p(dz, torch.float32, "dz"), _p(w2, torch.float32, "w2"), B, P, H, _p(dZ, torch.float32, "dZ"),
+                            _p(dU, torch.float32, "dU"), _p(gw2_part, torch.float32, "gw2_part"), _stream()),
+          "ctr_din_att_dz")
+
+
+def colsum_rows(part, out):
+    rows, ncols = part.shape
+    check(_L.ctr_colsum_rows(_p(part, torch.float32, "part"), rows, ncols, ncols, _p(out, torch.float32, "out"), _stream()),
+          "ctr_colsum_rows")
+
+
 def group_sum(dZ, B, P, N, dU):
     check(_L.ctr_group_sum(_p(dZ, torch.float32, "dZ"), B, P, N, _p(dU, torch.float32, "dU"), _stream()),
           "ctr_group_sum")
