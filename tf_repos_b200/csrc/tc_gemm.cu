@@ -148,6 +148,89 @@ constexpr int TC_STG_PITCH = TC_BM + 4;                          // epilogue sta
 constexpr int TC_STG_BYTES = TC_BM * TC_STG_PITCH * 4;
 constexpr int tc_smem_bytes(int stages) { return (stages * TC_STAGE_BYTES > TC_STG_BYTES ? stages * TC_STAGE_BYTES : TC_STG_BYTES) + 1024; }
 
+// ---- epilogue 2 (both kernels): NW warps write whole rows of the staged tile (lane l <-> columns 4l..4l+3, 512 B
+// coalesced): bias / group bias / relu / dropout (EPI 1), accumulate (EPI 2).  When a row needs a global read first
+// (dropout mask, old C) the reads of 4 rows are issued together: one dependent load per row made the masked forward of
+// DIN's attention layer latency-bound at 1.1 TB/s.
+template <int EPI, int NW>
+__device__ __forceinline__ void tc_epilogue_rows(const float* __restrict__ stg, float* __restrict__ Cz, int ldc, int M, int N,
+                                                 int i0, int j0, int n_here, int warp, int lane,
+                                                 const float* __restrict__ bias, int act, const float* __restrict__ mask,
+                                                 float keep, const float* __restrict__ gbias, int gP) {
+  const int col = lane * 4, gj = j0 + col;
+  const bool vec = ((ldc & 3) == 0) && ((((uintptr_t)Cz) & 15) == 0) && (EPI != 1 || !mask || ((((uintptr_t)mask) & 15) == 0));
+  if (col >= n_here) return;
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (EPI == 1 && bias) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bv[q] = (gj + q < N) ? bias[gj + q] : 0.f;
+  }
+  const int rows = min(TC_BM, M - i0);
+  const bool full = vec && (col + 4 <= n_here);
+  auto emit_row = [&](int row, const float4& mkv, const float4& ocv) {
+    const int gi = i0 + row;
+    const float4 t = *reinterpret_cast<const float4*>(stg + row * TC_STG_PITCH + col);
+    float v[4] = {t.x, t.y, t.z, t.w};
+    float* cp = Cz + (int64_t)gi * ldc + gj;
+    if (EPI == 2) {
+      if (full) { v[0] += ocv.x; v[1] += ocv.y; v[2] += ocv.z; v[3] += ocv.w; }
+      else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (col + q < n_here) v[q] += cp[q];
+      }
+    }
+    if (EPI == 1) {
+      const float* gb = gbias ? gbias + (int64_t)(gi / gP) * N + gj : nullptr;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[q] += bv[q];
+        if (gb && col + q < n_here) v[q] += gb[q];
+        if (act == 1) v[q] = fmaxf(v[q], 0.f);
+      }
+      if (mask) {
+        const float* mp = mask + (int64_t)gi * ldc + gj;
+        if (full) {
+          v[0] = __fdiv_rn(v[0], keep) * mkv.x; v[1] = __fdiv_rn(v[1], keep) * mkv.y;
+          v[2] = __fdiv_rn(v[2], keep) * mkv.z; v[3] = __fdiv_rn(v[3], keep) * mkv.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (col + q < n_here) v[q] = __fdiv_rn(v[q], keep) * mp[q];
+        }
+      }
+    }
+    if (full) {
+      *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (col + q < n_here) cp[q] = v[q];
+    }
+  };
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = f4_zero();
+  if (full && ((EPI == 1 && mask) || EPI == 2)) {
+    constexpr int UNR = 4;
+    for (int row_base = warp; row_base < rows; row_base += NW * UNR) {
+      float4 mk[UNR], oc[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int row = row_base + u * NW;
+        mk[u] = one; oc[u] = zero;
+        if (row < rows) {
+          const int64_t o = (int64_t)(i0 + row) * ldc + gj;
+          if (EPI == 1) mk[u] = __ldg(reinterpret_cast<const float4*>(mask + o));
+          if (EPI == 2) oc[u] = *reinterpret_cast<const float4*>(Cz + o);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int row = row_base + u * NW;
+        if (row < rows) emit_row(row, mk[u], oc[u]);
+      }
+    }
+  } else {
+    for (int row = warp; row < rows; row += NW) emit_row(row, one, zero);
+  }
+}
+
 // C[i][j] = sum_r A(i,r) * B(r,j)
 //   A_RC: A(i,r) = A[i*lda + r] else A[r*lda + i];  B_RC: B(r,j) = B[j*ldb + r] else B[r*ldb + j]
 // EPI 0: store (split-R chunk z to C + z*M*ldc)  1: act(acc + bias + gbias[i/gP]) (/keep*mask)  2: C += acc
@@ -261,56 +344,7 @@ tc_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
 
   // ---- epilogue 2: a warp writes whole rows (lane l <-> columns 4l..4l+3): 512 B coalesced stores
   float* Cz = C + (EPI == 0 ? (int64_t)blockIdx.z * M * ldc : 0);
-  const int col = lane * 4, gj = j0 + col;
-  const bool vec = ((ldc & 3) == 0) && ((((uintptr_t)Cz) & 15) == 0) && (EPI != 1 || !mask || ((((uintptr_t)mask) & 15) == 0));
-  if (col < n_here) {
-    float bv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (EPI == 1 && bias) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) bv[q] = (gj + q < N) ? bias[gj + q] : 0.f;
-    }
-    const int rows = min(TC_BM, M - i0);
-    for (int row = warp; row < rows; row += 4) {
-      const int gi = i0 + row;
-      const float4 t = *reinterpret_cast<const float4*>(stg + row * TC_STG_PITCH + col);
-      float v[4] = {t.x, t.y, t.z, t.w};
-      float* cp = Cz + (int64_t)gi * ldc + gj;
-      const bool full = vec && (col + 4 <= n_here);
-      if (EPI == 2) {
-        if (full) { const float4 o = *reinterpret_cast<const float4*>(cp); v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
-        else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) if (col + q < n_here) v[q] += cp[q];
-        }
-      }
-      if (EPI == 1) {
-        const float* gb = gbias ? gbias + (int64_t)(gi / gP) * N + gj : nullptr;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          v[q] += bv[q];
-          if (gb && col + q < n_here) v[q] += gb[q];
-          if (act == 1) v[q] = fmaxf(v[q], 0.f);
-        }
-        if (mask) {
-          const float* mp = mask + (int64_t)gi * ldc + gj;
-          if (full) {
-            const float4 mk = *reinterpret_cast<const float4*>(mp);
-            v[0] = __fdiv_rn(v[0], keep) * mk.x; v[1] = __fdiv_rn(v[1], keep) * mk.y;
-            v[2] = __fdiv_rn(v[2], keep) * mk.z; v[3] = __fdiv_rn(v[3], keep) * mk.w;
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (col + q < n_here) v[q] = __fdiv_rn(v[q], keep) * mp[q];
-          }
-        }
-      }
-      if (full) {
-        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (col + q < n_here) cp[q] = v[q];
-      }
-    }
-  }
+  tc_epilogue_rows<EPI, 4>(stg, Cz, ldc, M, N, i0, j0, n_here, warp, lane, bias, act, mask, keep, gbias, gP);
 }
 
 
@@ -562,56 +596,7 @@ tc_gemm_ws_kernel(const float* __restrict__ A, int lda, const float* __restrict_
 
   // ---------------- epilogue 2 (warps 0-7): whole rows, 512 B coalesced stores ----------------
   float* Cz = C + (EPI == 0 ? (int64_t)blockIdx.z * M * ldc : 0);
-  const int col = lane * 4, gj = j0 + col;
-  const bool vec = ((ldc & 3) == 0) && ((((uintptr_t)Cz) & 15) == 0) && (EPI != 1 || !mask || ((((uintptr_t)mask) & 15) == 0));
-  if (col < n_here) {
-    float bv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (EPI == 1 && bias) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) bv[q] = (gj + q < N) ? bias[gj + q] : 0.f;
-    }
-    const int rows = min(TC_BM, M - i0);
-    for (int row = warp; row < rows; row += 8) {
-      const int gi = i0 + row;
-      const float4 t = *reinterpret_cast<const float4*>(stg + row * TC_STG_PITCH + col);
-      float v[4] = {t.x, t.y, t.z, t.w};
-      float* cp = Cz + (int64_t)gi * ldc + gj;
-      const bool full = vec && (col + 4 <= n_here);
-      if (EPI == 2) {
-        if (full) { const float4 o = *reinterpret_cast<const float4*>(cp); v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
-        else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) if (col + q < n_here) v[q] += cp[q];
-        }
-      }
-      if (EPI == 1) {
-        const float* gb = gbias ? gbias + (int64_t)(gi / gP) * N + gj : nullptr;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          v[q] += bv[q];
-          if (gb && col + q < n_here) v[q] += gb[q];
-          if (act == 1) v[q] = fmaxf(v[q], 0.f);
-        }
-        if (mask) {
-          const float* mp = mask + (int64_t)gi * ldc + gj;
-          if (full) {
-            const float4 mk = *reinterpret_cast<const float4*>(mp);
-            v[0] = __fdiv_rn(v[0], keep) * mk.x; v[1] = __fdiv_rn(v[1], keep) * mk.y;
-            v[2] = __fdiv_rn(v[2], keep) * mk.z; v[3] = __fdiv_rn(v[3], keep) * mk.w;
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (col + q < n_here) v[q] = __fdiv_rn(v[q], keep) * mp[q];
-          }
-        }
-      }
-      if (full) {
-        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (col + q < n_here) cp[q] = v[q];
-      }
-    }
-  }
+  tc_epilogue_rows<EPI, 8>(stg, Cz, ldc, M, N, i0, j0, n_here, warp, lane, bias, act, mask, keep, gbias, gP);
 }
 
 template <bool A_RC, bool B_RC, int EPI>
