@@ -481,7 +481,7 @@ def main_b200(args):
                           "note": "gathered rows only (LazyAdam-like): NOT TensorFlow's result; context only"}
 
         def infer(i):
-            model.predict(devb[i % N_BATCHES][0], devb[i % N_BATCHES][1])
+            (model.predict_graphed if use_graphs else model.predict)(devb[i % N_BATCHES][0], devb[i % N_BATCHES][1])
         ms_inf = timed(infer, args.steps, 3)
         extras["infer"] = {"value": world * B * args.steps / (ms_inf * 1e-3), "unit": "samples/s",
                            "ms_per_step": ms_inf / args.steps}

@@ -71,6 +71,10 @@ def test_graph_replayed_steps_equal_eager_steps(mode, P):
         for sa, sb in zip(ta.slots, tb.slots):
             assert torch.equal(sa, sb)
     assert torch.equal(a.dense.flat, b.dense.flat) and a.global_step == b.global_step
+    ids, vals, _ = synth.criteo_batch(512, 50_000, 39, seed=99, device="cuda")
+    want = a.predict(ids, vals).clone()
+    for _ in range(3):                      # eager visit, capture, replay
+        assert torch.equal(b.predict_graphed(ids, vals), want)
 
 
 def _park(model, kind, seed):
