@@ -208,7 +208,7 @@ def main_reference(args):
     # three warm-up steps (first touches of the table-sized scratch arrays) and a wall-clock budget: a
     # full-vocabulary CPU step takes seconds
     wu = max(min(args.warmup, 3), 1)
-    sps, ms, done, cores, desc = run_cpu(args.steps, wu, 150.0, args.vocab, args.batch)
+    sps, ms, done, cores, desc = run_cpu(args.steps, wu, 100.0, args.vocab, args.batch)
     line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": done, "warmup": wu, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -2,7 +2,7 @@
 CPU with exact rationals: r = refine(seed 1/b); q = RN(a*r); t = RN(a - b*q) [one FMA]; result = RN(q + r*t) [one FMA].
 With a correctly rounded seed the sequence returns the correctly rounded quotient over the WHOLE guarded range
 (|a| in [2^-100, 2^60), b in [2^-51, 2^21)) -- in particular the FMA residual stays exactly representable down to
-|a| = 2^-100 -- and the staged power-of-two scaling extends it to denormal numerators.  (How the hardware's MUFU.RCP seed
+|a| = 2^-100 -- and the power-of-two scaling of the packed sweep's S loops (csrc/adam_packed.cuh) extends it to denormal numerators.  (How the hardware's MUFU.RCP seed
 behaves is what ctr_selftest_divsqrt checks on the GPU; this test pins the range reasoning.)"""
 import random
 import struct

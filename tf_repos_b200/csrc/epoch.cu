@@ -513,16 +513,6 @@ __global__ void __launch_bounds__(256) selftest_divsqrt_kernel(uint64_t seed, in
     if (__float_as_uint(div_rn_inrange(a, b)) != __float_as_uint(__fdiv_rn(a, b))) ++bad_d;
     // a zero numerator: the fast path must give a zero (either sign: see adam_untouched)
     if (div_rn_inrange((r0 >> 62) & 1 ? -0.f : 0.f, b) != 0.f) ++bad_d;
-#ifdef CTR_SCALED_FASTPATH
-    {  // staged scaled path: tiny / denormal numerators over small denominators
-      const uint32_t dm = (uint32_t)(r1 >> 8) & 0x7FFFFFu;
-      float as = ((r1 >> 40) & 3) ? __uint_as_float(dm ? dm : 1u) : test_float(r1 >> 1, -126, -101);   // 3/4 denormals
-      if (r1 >> 63) as = -as;
-      const float bs = test_float(r2, -50, -26);
-      const float got = __fmul_rn(div_rn_inrange(__fmul_rn(as, 18446744073709551616.f), bs), 5.421010862427522e-20f);
-      if (__float_as_uint(got) != __float_as_uint(__fdiv_rn(as, bs))) ++bad_d;
-    }
-#endif
   }
   if (bad_s) atomicAdd(&mism[0], bad_s);
   if (bad_d) atomicAdd(&mism[1], bad_d);
