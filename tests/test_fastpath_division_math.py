@@ -86,3 +86,21 @@ def test_scaled_division_handles_denormal_numerators():
         q = rn32(Fraction(float(div_fast(a_s, b))) * Fraction(1, 2 ** 64))
         want = rn32(Fraction(float(a)) / Fraction(float(b)))
         assert abs(float(want)) >= 2.0 ** -126 and want.tobytes() == q.tobytes(), (a, b, want, q)
+
+
+def test_scaled_sqrt_handles_denormal_and_zero_second_moments():
+    """Loop S2 of the packed sweep (csrc/adam_packed.cuh): sqrt(v) for a denormal v is taken as sqrt(v*2^48)*2^-24 --
+    the up-scaling is exact, the correctly rounded root of the scaled operand is a normal number and the down-scaling
+    is exact -- and v == 0 is clamped to 2^-101 before the root: sqrt(0)+eps must still be eps for eps >= 2^-40."""
+    rng = random.Random(3)
+    for _ in range(4000):
+        bits = rng.randint(1, 0x7FFFFF) >> rng.randint(0, 22)              # denormals of every magnitude
+        v = np.array([max(bits, 1)], dtype=np.uint32).view(np.float32)[0]
+        want = np.sqrt(v)                                                   # numpy's float32 sqrt is IEEE (correctly rounded)
+        vs = np.float32(float(v) * 2.0 ** 48)
+        assert float(vs) == float(v) * 2.0 ** 48 and float(vs) >= 2.0 ** -101
+        got = np.float32(float(np.sqrt(vs)) * 2.0 ** -24)
+        assert got.tobytes() == want.tobytes(), (v, got, want)
+    for eps in (np.float32(1e-8), np.float32(2.0 ** -40), np.float32(2.0 ** -26)):
+        clamp_root = np.float32(float(np.sqrt(np.float32(2.0 ** -101))) * 2.0 ** -24)
+        assert np.float32(clamp_root + eps).tobytes() == eps.tobytes()       # == sqrt(0) + eps
