@@ -125,6 +125,7 @@ class ShardedDeepFM:
         ops.shard_keys(ids.reshape(-1), self.N, G, self.keys[:n], self.oob)
         ops.unique_segment(self.keys[:n], self.uw)          # uw.inverse[i] = cache position of occurrence i
         ops.shard_split(self.uw.uniq, self.uw.n_uniq, n, self.N, G, self.counts, self.local_ids)
+        self._mark("keys+sort+split")
         if G > 1:   # every rank's bucket sizes in one collective, one host sync per step
             dist.all_gather_into_tensor(self.count_mat, self.counts, group=self.group)
             cm = self.count_mat.view(G, G).tolist()
@@ -134,14 +135,19 @@ class ShardedDeepFM:
             send = self.counts.tolist()
             recv = list(send)
         U, R = sum(send), sum(recv)
+        self._mark("count all-gather + host sync")
         self._a2a(self.recv_ids[:R], self.local_ids[:U], recv, send)
+        self._mark("a2a ids")
         if deferred_j is not None:   # owners bring the requested rows to the start of this step
             self.updater.unique(self.recv_ids[:R])
             self.updater.epoch_rows([(t, None) for t in self.tables], deferred_j, apply=False)
+        self._mark("owner: unique + catch-up rows")
         ops.gather_scale_rows(self.recv_ids[:R], None, self.V.var, self.rows_v, 1, self.K, self.oob)
         ops.gather_scalar(self.recv_ids[:R], self.W.var, self.rows_w[:R])
+        self._mark("owner: gather rows")
         self._a2a(self.cache_v[:U], self.rows_v[:R], send, recv)
         self._a2a(self.cache_w[:U], self.rows_w[:R], send, recv)
+        self._mark("a2a rows (v, w)")
         return U, send, recv, R
 
     def _forward(self, ids, vals, U, train, masks=None):
@@ -191,6 +197,27 @@ class ShardedDeepFM:
 
     use_graphs = True
 
+    # ---- optional per-phase device timing (CTR_SHARD_PHASES=1; tools/time_shard_phases.py) ---------------------
+    _ph = None
+
+    def _mark(self, name):
+        if self._ph is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._ph.append((name, ev))
+
+    def phase_report(self):
+        """{phase: mean ms} over the steps recorded since _ph was set to []"""
+        torch.cuda.synchronize()
+        tot, cnt = {}, {}
+        for (n0, e0), (n1, e1) in zip(self._ph[:-1], self._ph[1:]):
+            if n1 == "begin":
+                continue
+            tot[n1] = tot.get(n1, 0.0) + e0.elapsed_time(e1); cnt[n1] = cnt.get(n1, 0) + 1
+        steps = max(sum(1 for n, _ in self._ph if n == "begin"), 1)
+        return {k: v / steps for k, v in tot.items()}
+
     def predict(self, ids, vals):
         B = ids.shape[0]
         assert B == self.B
@@ -206,6 +233,7 @@ class ShardedDeepFM:
         n = B * F
         deferred = self.update_mode == "exact_deferred"
         upd = self.updater
+        self._mark("begin")
         if deferred:
             j = self.epoch_pos
             if j == 0:
@@ -215,10 +243,12 @@ class ShardedDeepFM:
             self.opt.tick()
         U, send, recv, R = self._lookup(ids, deferred_j=(self.epoch_pos if deferred else None))
         self._compute(vals, labels, masks)
+        self._mark("compute segment (K1, MLP, loss, K2, seg sums)")
         self._a2a(self.recv_g[:R], self.g_cache[:U], recv, send)
         self._a2a(self.recv_gw[:R], self.gw_cache[:U], recv, send)
         if G > 1:
             dist.all_reduce(self.dense.grad, group=self.group)
+        self._mark("a2a grads (v, w) + all-reduce dense")
         if deferred:
             # upd.uw already holds unique(recv_ids) from the catch-up
             upd.segment_sum(self.recv_g[:R], self.recv_gw[:R])
@@ -230,8 +260,10 @@ class ShardedDeepFM:
         else:
             upd.dedup(self.recv_ids[:R], self.recv_g[:R], self.recv_gw[:R])
             upd.apply(self.V, self.W, exact=(self.update_mode == "exact"), l2_reg=self.l2_reg)
+        self._mark("owner: seg sums + row apply (+ sweep at epoch end)")
         self.dense.apply()
         self.global_step += 1
+        self._mark("dense apply")
         return torch.cat([self.loss_ce, upd.reg[1:2], upd.reg[0:1]])   # reg terms: this rank's shard only
 
     def check_ids(self):
