@@ -190,7 +190,9 @@ int ctr_epoch_rows2(int opt, int apply, float* var, float* slot0, float* slot1, 
  * ss_partials: device double[ctr_epoch_max_steps()][*n_partials_host].
  * list / list_cap / list_count / ss_rows (optional, Adam): scratch for the packed-pipe sweep (csrc/epoch_adam.cu):
  * device int32[list_cap] with list_cap >= min(n_rows, ids gathered since `from`), a device int32 counter, and the
- * row kernels' per-step sum(var^2) accumulator (the `ss` of ctr_epoch_rows).  NULL selects the scalar kernels. */
+ * row kernels' per-step sum(var^2) accumulator (the `ss` of ctr_epoch_rows).  NULL selects the scalar kernels.
+ * *list_count returns the number of gathered rows found; if it exceeds list_cap the precondition was violated and
+ * the rows beyond list_cap were NOT caught up (the engine sizes the list so that this cannot happen). */
 int ctr_epoch_sweep(int opt, float* var, float* slot0, float* slot1, uint8_t* last, int64_t n_rows, int K,
                     const float* hyper, const float* lr_table, int from, int upto, int reset, double* ss_partials,
                     int* n_partials_host, int32_t* list, int64_t list_cap, int32_t* list_count, double* ss_rows,
