@@ -187,7 +187,8 @@ int ctr_epoch_rows2(int opt, int apply, float* var, float* slot0, float* slot1, 
 /* All rows -> state after `upto` steps of this epoch.  Rows whose `last` byte equals `from` (nothing gathered
  * them since the previous sweep; from = 0 after an epoch-end sweep) replay steps from..upto-1; the others replay
  * last..upto-1.  reset != 0: epoch end, every `last` byte returns to 0; reset == 0: mid-epoch flush, `last` = upto.
- * ss_partials: device double[ctr_epoch_max_steps()][*n_partials_host], ZERO-INITIALISED ONCE by the caller: a call
+ * ss_partials: device double[ctr_epoch_max_steps()][*n_partials_host] (*n_partials_host is always
+ * 6 * ctr_device_sm_count(), so it can be sized before the first call), ZERO-INITIALISED ONCE by the caller: a call
  * rewrites, for every step < upto, one entry per CTA it launches (fewer than *n_partials_host) and ctr_epoch_reg_loss
  * sums whole rows, so the entries no CTA owns must hold 0.
  * list / list_cap / list_count / ss_rows (optional, Adam): scratch for the packed-pipe sweep (csrc/epoch_adam.cu):
