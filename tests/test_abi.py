@@ -48,3 +48,55 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
         assert "no CPU/eager fallback" in str(e)
     else:
         raise AssertionError("loading a missing library must raise")
+
+
+def _c_kind(decl: str):
+    """'const float* x' -> 'ptr'; 'int64_t n' -> ctypes.c_int64 ..."""
+    decl = decl.strip()
+    if "*" in decl or decl.startswith("ctr_stream_t"):
+        return "ptr"
+    words = decl.replace("const", " ").split()
+    base = " ".join(words[:-1]) if len(words) > 1 else words[0]
+    return {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
+            "size_t": ctypes.c_size_t, "float": ctypes.c_float, "double": ctypes.c_double, "void": None}[base]
+
+
+def _py_kind(t):
+    if t is None:
+        return None
+    if t in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(t, ctypes._Pointer):
+        return "ptr"
+    return t
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/ctr_b200.h against tf_repos_b200/_lib.py::SIGNATURES: same number of arguments, same
+    width and kind (pointer / int / int64 / size_t / float) in every position, same return type -- a mismatch here would
+    pass garbage through the boundary without any error."""
+    from tf_repos_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "ctr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//.*", "", text)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(ctr_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text)
+    assert len(protos) == len(_declared_symbols())
+    for ret, name, args in protos:
+        res, sig = _lib.SIGNATURES[name]
+        want = [] if args.strip() in ("", "void") else [_c_kind(a) for a in args.split(",")]
+        got = [_py_kind(t) for t in sig]
+        assert got == want, (name, got, want)
+        assert _py_kind(res) == _c_kind(ret + " x"), (name, res, ret)
+
+
+def test_integration_md_binding_snippet_matches_the_header():
+    """The reference-side ctypes stub shown in INTEGRATION.md §2 must bind the real prototype (it is documentation a
+    maintainer copies): run its binding lines and compare the argtypes with SIGNATURES."""
+    from tf_repos_b200 import _lib
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = md.split("## 2.")[1].split("```python")[1].split("```")[0]
+    binding = block.split("def fm_forward")[0].replace('"tf_repos_b200/libctr_b200.so"', repr(_lib.LIB_PATH))
+    ns = {}
+    exec(binding, ns)                                   # import ctypes, torch; CDLL; argtypes -- no compute call
+    got = [_py_kind(t) for t in ns["L"].ctr_fm_embed_fwd.argtypes]
+    assert got == [_py_kind(t) for t in _lib.SIGNATURES["ctr_fm_embed_fwd"][1]]
+    call = block.split("L.ctr_fm_embed_fwd(")[1].split(")\n")[0]
+    assert len([a for a in re.split(r",(?![^()]*\))", call) if a.strip()]) == len(got)
